@@ -1,0 +1,153 @@
+"""Pin the CPU oracle (oracle/piv_oracle.py) to the golden vectors produced by the
+unmodified reference (tests/golden/make_golden.py).  CPU only.
+
+Tolerances: the reference's first pass is float64 -> 1e-9 px; later passes are float32
+FFTs (torch's FFT backend vs scipy's pocketfft differ in rounding) -> 2e-5 px; masks and
+the integer/byte window-shift functions must be identical."""
+import numpy as np
+import pytest
+
+import cases
+from oracle import piv_oracle as O
+
+TOL64 = 1e-9
+TOL32 = 2e-5
+
+
+def test_inputs_reproducible(golden):
+    g = golden("pass1.npz")
+    a, b = cases.small_pair(seed=1, kind="uniform")
+    assert cases.sha(a, b) == str(g["uniform_sha"])
+    a, b = cases.small_pair(seed=1, kind="vortex", zero_patch=True)
+    assert cases.sha(a, b) == str(g["vortex_sha"])
+
+
+@pytest.mark.parametrize("kind,zero", [("uniform", False), ("vortex", True)])
+@pytest.mark.parametrize("w,o", cases.PASS1_GEOMS)
+def test_pass1(golden, kind, zero, w, o):
+    g = golden("pass1.npz")
+    a, b = cases.small_pair(seed=1, kind=kind, zero_patch=zero)
+    u, v, x, y, m = O.extended_search_area_piv(a, b, w, o, validate=True)
+    assert np.array_equal(m, g[f"{kind}_{w}_{o}_mask"])
+    assert np.array_equal(x, g[f"{kind}_{w}_{o}_x"]) and np.array_equal(y, g[f"{kind}_{w}_{o}_y"])
+    assert np.abs(u - g[f"{kind}_{w}_{o}_u"]).max() < TOL64
+    assert np.abs(v - g[f"{kind}_{w}_{o}_v"]).max() < TOL64
+
+
+def test_pass1_no_validation(golden):
+    g = golden("pass1.npz")
+    a, b = cases.small_pair(seed=1)
+    u, v, x, y, m = O.extended_search_area_piv(a, b, 32, 16, validate=False)
+    assert m is None
+    assert np.abs(u - g["noval_32_16_u"]).max() < TOL64
+    assert np.abs(v - g["noval_32_16_v"]).max() < TOL64
+
+
+def test_pass1_errors():
+    a, b = cases.small_pair(seed=1)
+    with pytest.raises(ValueError):
+        O.extended_search_area_piv(a, b, 32, 32)
+    with pytest.raises(ValueError):
+        O.extended_search_area_piv(a, b, 512, 0)
+
+
+@pytest.mark.parametrize("mode", ["CWS", "DWS"])
+@pytest.mark.parametrize("kind", ["uniform", "vortex"])
+def test_multipass_function_boundary(golden, mode, kind):
+    """Each pass is fed the REFERENCE's previous-pass output, so errors do not chain."""
+    g = golden(f"multipass_{mode}.npz")
+    a, b = cases.small_pair(seed=2, kind=kind)
+    assert cases.sha(a, b) == str(g[f"{kind}_sha"])
+    x, y = O.get_coordinates(a.shape, 64, 32)
+    w, o = 64, 32
+    for it in (1, 2):
+        u0, v0, m0 = (g[f"{kind}_p{it-1}_{k}"].copy() for k in ("u", "v", "mask"))
+        w, o = w // 2, o // 2
+        fn = O.ITER_MODES[mode](a.shape, w, o)
+        u, v, x1, y1, m = fn(a, b, x, y, u0, v0, m0)
+        assert np.array_equal(m, g[f"{kind}_p{it}_mask"])
+        assert np.array_equal(x1, g[f"{kind}_p{it}_x"]) and np.array_equal(y1, g[f"{kind}_p{it}_y"])
+        for got, key in ((u, "u"), (v, "v")):
+            err = np.abs(got - g[f"{kind}_p{it}_{key}"])
+            # float32 FFT backends differ in rounding; ill-conditioned fits (flat 16 px peaks)
+            # amplify that, so: 99 % within 2e-5 px, everything within the 1e-3 px north-star bound
+            assert np.quantile(err, 0.99) < TOL32 and err.max() < 1e-3
+        x, y = x1, y1
+
+
+@pytest.mark.parametrize("mode", ["CWS", "DWS"])
+def test_multipass_without_mask(golden, mode):
+    g = golden(f"multipass_{mode}.npz")
+    a, b = cases.small_pair(seed=2)
+    x, y = O.get_coordinates(a.shape, 64, 32)
+    fn = O.ITER_MODES[mode](a.shape, 32, 16)
+    u, v, _, _, m = fn(a, b, x, y, g["uniform_p0_u"].copy(), g["uniform_p0_v"].copy(), None)
+    assert m is None
+    assert np.abs(u - g["noval_p1_u"]).max() < TOL32
+    assert np.abs(v - g["noval_p1_v"]).max() < TOL32
+
+
+@pytest.mark.parametrize("w,o", [(32, 16), (16, 8), (64, 32)])
+def test_window_shifts_bit_exact(golden, w, o):
+    g = golden("shift.npz")
+    a, vx, vy = cases.shift_case(seed=w, w=w, ovl=o)
+    assert cases.sha(a, vx, vy) == str(g[f"in_{w}_sha"])
+    idx = O.window_index_grid(a.shape, w, o)
+    r = O.bilinear_interpolation_cws(a, idx, vx[:, None, None], vy[:, None, None])
+    assert r.dtype == np.float32
+    assert cases.sha(r) == str(g[f"cws_{w}_sha"])
+    assert np.array_equal(r[:6], g[f"cws_{w}_head"])
+    ix, iy = np.rint(vx).astype(np.int64), np.rint(vy).astype(np.int64)
+    r = O.interpolation_dws(a, idx, ix[:, None, None], iy[:, None, None])
+    assert r.dtype == np.uint8
+    assert cases.sha(r) == str(g[f"dws_{w}_sha"])
+
+
+@pytest.mark.parametrize("w,dt", [(16, np.float32), (64, np.float32), (16, np.float64),
+                                  (32, np.float64)])
+def test_correlation_to_displacement_adversarial(golden, w, dt):
+    g = golden("corr2disp.npz")
+    tag = f"{w}_{np.dtype(dt).name}"
+    maps = cases.adversarial_maps(seed=w + (dt == np.float64), c=400, w=w, dtype=dt)
+    assert cases.sha(maps) == str(g[f"{tag}_sha"])
+    u, v, m = O.correlation_to_displacement(maps.copy(), 20, 20, True)
+    assert np.array_equal(m, g[f"{tag}_mask"])
+    # identical inputs, float64 log fit: only libm-vs-ATen log differences remain
+    assert np.abs(u - g[f"{tag}_u"]).max() < 1e-9
+    assert np.abs(v - g[f"{tag}_v"]).max() < 1e-9
+
+
+def test_correlate_fft_uint8_promotes_to_float32(golden):
+    g = golden("corr2disp.npz")
+    a, b = cases.small_pair(seed=4)
+    corr = O.correlate_fft(O.moving_window_array(a, 32, 16), O.moving_window_array(b, 32, 16))
+    assert corr.dtype == np.float32
+    ref = g["corr_u8_32_head"]
+    assert np.abs(corr[:4] - ref).max() <= 2e-6 * np.abs(ref).max()
+    assert np.allclose(corr.sum(axis=(1, 2), dtype=np.float64), g["corr_u8_32_sum"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("cws2", dict(wind_size=64, overlap=32, multipass=2, multipass_mode="CWS", dt=12, scale=0.02)),
+    ("dws2", dict(wind_size=64, overlap=32, multipass=2, multipass_mode="DWS", dt=12, scale=0.02)),
+    ("cws3", dict(wind_size=64, overlap=32, multipass=3, multipass_mode="CWS", dt=1, scale=1.0)),
+    ("single", dict(wind_size=32, overlap=16, multipass=1, dt=1, scale=1.0)),
+])
+def test_offline_pipeline(golden, tag, kw):
+    """Whole OfflinePIV generator output (passes chained + scipy/Qhull hole filling)."""
+    g = golden("offline.npz")
+    pairs = [cases.small_pair(seed=10 + i, kind="uniform" if i % 2 == 0 else "vortex")
+             for i in range(3)]
+    assert cases.sha(*[f for p in pairs for f in p]) == str(g["in_sha"])
+    assert tuple(g[f"{tag}_n"]) == (3, 3)
+    for i, (a, b) in enumerate(pairs):
+        out = O.offline_piv_pair(a, b, **kw)
+        assert out is not None
+        x, y, u, v = out
+        assert np.array_equal(x, g[f"{tag}_{i}_x"]) and np.array_equal(y, g[f"{tag}_{i}_y"])
+        # velocities are px * scale / dt * 1000; tolerance in px units
+        k = kw["scale"] / kw["dt"] * 1000
+        du = np.abs(u - g[f"{tag}_{i}_u"]) / k
+        dv = np.abs(v - g[f"{tag}_{i}_v"]) / k
+        assert np.quantile(du, 0.99) < 1e-4 and np.quantile(dv, 0.99) < 1e-4
+        assert du.max() < 5e-2 and dv.max() < 5e-2   # chained float32 passes near invalid vectors
