@@ -1,0 +1,62 @@
+// Host-side launcher of the fused pass kernels; one translation unit per window size
+// (fused_w64.cu / fused_w32.cu / fused_w16.cu) so they compile in parallel.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "piv_params.h"
+
+namespace pivb200 {
+
+// returns a cudaError_t (0 = ok); -1 if the (loader, sink) combination is not built
+int launch_fused_w64(int loader, int sink, const CUtensorMap& ta, const CUtensorMap& tb,
+                     const PassParams& p, cudaStream_t stream);
+int launch_fused_w32(int loader, int sink, const CUtensorMap& ta, const CUtensorMap& tb,
+                     const PassParams& p, cudaStream_t stream);
+int launch_fused_w16(int loader, int sink, const CUtensorMap& ta, const CUtensorMap& tb,
+                     const PassParams& p, cudaStream_t stream);
+
+void count_launch();
+
+}  // namespace pivb200
+
+#ifdef PIVB200_FUSED_IMPL
+#include "piv_fused.cuh"
+
+namespace pivb200 {
+
+template <int W, int LOADER, int SINK>
+static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const PassParams& p,
+                      cudaStream_t stream) {
+    using S = Smem<W, LOADER>;
+    auto kern = piv_fused_kernel<W, LOADER, SINK>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (err != cudaSuccess) return static_cast<int>(err);
+    int dev = 0, sms = 0, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, S::TOTAL);
+    if (err != cudaSuccess) return static_cast<int>(err);
+    if (occ < 1) occ = 1;
+    const long long njobs = (p.n_total + Geo<W>::NW - 1) / Geo<W>::NW;
+    long long grid = static_cast<long long>(occ) * sms;
+    if (grid > njobs) grid = njobs;
+    kern<<<static_cast<unsigned>(grid), 32, S::TOTAL, stream>>>(ta, tb, p);
+    count_launch();
+    return static_cast<int>(cudaGetLastError());
+}
+
+template <int W>
+static int launch_w(int loader, int sink, const CUtensorMap& ta, const CUtensorMap& tb,
+                    const PassParams& p, cudaStream_t stream) {
+    if (sink == SK_DISP && loader == LD_FRAME_INT) return launch_one<W, LD_FRAME_INT, SK_DISP>(ta, tb, p, stream);
+    if (sink == SK_DISP && loader == LD_FRAME_CWS) return launch_one<W, LD_FRAME_CWS, SK_DISP>(ta, tb, p, stream);
+    if (sink == SK_WIN && loader == LD_FRAME_INT) return launch_one<W, LD_FRAME_INT, SK_WIN>(ta, tb, p, stream);
+    if (sink == SK_WIN && loader == LD_FRAME_CWS) return launch_one<W, LD_FRAME_CWS, SK_WIN>(ta, tb, p, stream);
+    if (sink == SK_CORR && loader == LD_EXPL_F32) return launch_one<W, LD_EXPL_F32, SK_CORR>(ta, tb, p, stream);
+    if (sink == SK_CORR && loader == LD_EXPL_U8) return launch_one<W, LD_EXPL_U8, SK_CORR>(ta, tb, p, stream);
+    return -1;
+}
+
+}  // namespace pivb200
+#endif

@@ -1,0 +1,73 @@
+"""Per-pair host post-processing of the final vector field (NumPy / SciPy, float64).
+
+Same behaviour as the tail of the reference's ``OfflinePIV.__call__`` (PIVbackend.py:884-900):
+invalid vectors -> NaN, linear fill along the four borders (``interpolate_boarders``,
+PIVbackend.py:328-344), Delaunay-linear fill of the remaining holes from the ring of valid
+neighbours (``fillMissingValues`` / ``getPixelsForInterp``, PIVbackend.py:266-308), vertical
+flip, sign of v, physical units.  The field is a few thousand vectors; this is not on the
+GPU hot path."""
+from __future__ import annotations
+
+import numpy as np
+from scipy.interpolate import LinearNDInterpolator
+
+__all__ = ["fill_borders", "fill_holes", "finalize_field"]
+
+
+def fill_borders(field: np.ndarray) -> np.ndarray:
+    """In-place 1-D linear interpolation of NaNs on the first/last row and column.  An edge
+    that is entirely NaN is left alone; NaNs beyond the outermost valid sample take its value."""
+    if not np.isnan(field).any():
+        return field
+    edges = (field[0, :], field[-1, :], field[:, 0], field[:, -1])
+    for edge in edges:                      # views: assignments write through to `field`
+        bad = np.isnan(edge)
+        if bad.all() or not bad.any():
+            continue
+        where = np.flatnonzero
+        edge[bad] = np.interp(where(bad), where(~bad), edge[~bad])
+    return field
+
+
+def _neighbour_ring(invalid: np.ndarray) -> np.ndarray:
+    """Valid cells that touch an invalid one through an edge (3x3 plus-shaped dilation of the
+    invalid set with a zero border, minus the set itself)."""
+    grown = invalid.copy()
+    grown[1:] |= invalid[:-1]
+    grown[:-1] |= invalid[1:]
+    grown[:, 1:] |= invalid[:, :-1]
+    grown[:, :-1] |= invalid[:, 1:]
+    return grown & ~invalid
+
+
+def fill_holes(field: np.ndarray):
+    """Fill NaNs by piecewise-linear (Delaunay) interpolation over the ring of valid neighbours.
+    Returns None -- the caller then skips the pair, as the reference does -- when the ring is
+    empty (no invalid vector at all), when the triangulation fails, or when the ring covers a
+    quarter of the field or more ("too many false vectors")."""
+    invalid = np.isnan(field)
+    ring = _neighbour_ring(invalid)
+    support = np.argwhere(ring)
+    if not support.size < ring.size / 2:
+        print("Warning! to many false vectors")
+        return None
+    try:
+        interp = LinearNDInterpolator(support, field[ring])
+        field[invalid] = interp(np.argwhere(invalid))
+    except Exception:
+        return None
+    return field
+
+
+def finalize_field(u, v, x, y, invalid, scale: float = 1.0, dt: float = 1.0):
+    """u, v in px (float64, modified in place) -> (x, y, u, v) in mm and m/s, or None to skip."""
+    if invalid is not None:
+        u[invalid] = np.nan
+        v[invalid] = np.nan
+        u = fill_holes(fill_borders(u))
+        v = fill_holes(fill_borders(v))
+        if u is None or v is None:
+            return None
+    u = np.flip(u, axis=0) * scale / dt * 1000
+    v = -np.flip(v, axis=0) * scale / dt * 1000
+    return x * scale, y * scale, u, v
