@@ -30,18 +30,16 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const PassPa
                       cudaStream_t stream) {
     using S = Smem<W, LOADER>;
     auto kern = piv_fused_kernel<W, LOADER, SINK>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::CTA_BYTES);
     if (err != cudaSuccess) return static_cast<int>(err);
-    int dev = 0, sms = 0, occ = 0;
+    int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, S::TOTAL);
-    if (err != cudaSuccess) return static_cast<int>(err);
-    if (occ < 1) occ = 1;
+    // persistent: one CTA of NWARPS warps per SM, each warp strides over the jobs
     const long long njobs = (p.n_total + Geo<W>::NW - 1) / Geo<W>::NW;
-    long long grid = static_cast<long long>(occ) * sms;
-    if (grid > njobs) grid = njobs;
-    kern<<<static_cast<unsigned>(grid), 32, S::TOTAL, stream>>>(ta, tb, p);
+    long long grid = (njobs + S::NWARPS - 1) / S::NWARPS;
+    if (grid > sms) grid = sms;
+    kern<<<static_cast<unsigned>(grid), S::NWARPS * 32, S::CTA_BYTES, stream>>>(ta, tb, p);
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }

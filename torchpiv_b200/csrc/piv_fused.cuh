@@ -103,10 +103,17 @@ struct Smem {
     static constexpr int XW = (LOADER == LD_FRAME_CWS) ? G::NW * 2 * W * 8 : 0;
     static constexpr int XF_OFF = XW_OFF + XW;                               // int    [NW][2][W]
     static constexpr int XF = (LOADER == LD_FRAME_CWS) ? G::NW * 2 * W * 4 : 0;
-    static constexpr int TD_OFF = XF_OFF + XF;                               // int [NW][2]: byte offset d of each tile
-    static constexpr int TD = T::kFrame ? G::NW * 2 * 4 : 0;
+    static constexpr int TD_OFF = ((XF_OFF + XF + 15) / 16) * 16;            // TileDesc [2][NW][2]: per (window, frame), double buffered
+    static constexpr int TD = T::kFrame ? 2 * G::NW * 2 * 32 : 0;
     static constexpr int BAR_OFF = ((TD_OFF + TD + 7) / 8) * 8;
     static constexpr int TOTAL = BAR_OFF + 8;
+    // One CTA per SM made of NWARPS independent warps (each with its own STRIDE bytes of smem)
+    // that walk the phases in lock step, so the SM fetches the (large, fully unrolled) instruction
+    // stream once per CTA instead of once per warp.
+    static constexpr int STRIDE = ((TOTAL + 255) / 256) * 256;
+    static constexpr int SMEM_MAX = 232448;           // 227 KB opt-in limit per CTA
+    static constexpr int NWARPS = (SMEM_MAX / STRIDE) > 16 ? 16 : (SMEM_MAX / STRIDE);
+    static constexpr int CTA_BYTES = NWARPS * STRIDE;
 };
 
 // ----------------------------------------------------------------------------------------
@@ -199,6 +206,17 @@ __device__ __forceinline__ float clamp_shift(float v) {
     return fminf(fmaxf(v, -static_cast<float>(kShiftClamp)), static_cast<float>(kShiftClamp));
 }
 
+// Everything the kernel needs to know about one (window, frame) tile; computed once per job by
+// one lane (integer divisions!) and broadcast through shared memory.
+struct __align__(16) TileDesc {
+    int pair;       // pair index = TMA z coordinate
+    int oy, ox;     // tile origin (absolute pixel) = window origin + integer part of the signed shift
+    int d;          // byte offset of the origin inside the staged tile row (ox & 15 via TMA, 0 via gather)
+    float vy, vx;   // signed float shift of this frame (CWS), 0 otherwise
+    int r0, c0;     // window origin
+};
+static_assert(sizeof(TileDesc) == 32, "TileDesc layout");
+
 // signed shift of `frame` (0 = a: minus, 1 = b: plus) and the tile origin it implies
 template <int LOADER>
 __device__ __forceinline__ void frame_origin(const PassParams& p, int g, const WinGeo& w, int frame,
@@ -225,7 +243,7 @@ __device__ __forceinline__ void frame_origin(const PassParams& p, int g, const W
 // the kernel
 // ----------------------------------------------------------------------------------------
 template <int W, int LOADER, int SINK>
-__global__ void __launch_bounds__(32) piv_fused_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_kernel(const __grid_constant__ CUtensorMap tmA,
                                                        const __grid_constant__ CUtensorMap tmB,
                                                        const PassParams p) {
     using G = Geo<W>;
@@ -235,10 +253,13 @@ __global__ void __launch_bounds__(32) piv_fused_kernel(const __grid_constant__ C
     constexpr int NW = G::NW, HALF = G::HALF, LOGW = G::LOGW, PM = G::PM, PQ = G::PQ, PC = G::PC;
     constexpr unsigned FULL = 0xffffffffu;
 
-    extern __shared__ __align__(1024) unsigned char smem[];
-    const int lane = threadIdx.x;
+    extern __shared__ __align__(1024) unsigned char smem_cta[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    unsigned char* smem = smem_cta + warp * S::STRIDE;       // this warp's private region
     const int n_total = static_cast<int>(p.n_total);
     const int njobs = (n_total + NW - 1) / NW;
+    const int job_stride = gridDim.x * S::NWARPS;
     const uint32_t bar = smem_u32(smem + S::BAR_OFF);
     uint32_t parity = 0;
     bool pending = false;
@@ -249,34 +270,40 @@ __global__ void __launch_bounds__(32) piv_fused_kernel(const __grid_constant__ C
     }
 
     // ---- request / gather the input tiles of one job -----------------------------------
-    auto stage_tiles = [&](int job) {
+    // buf: which half of the double-buffered descriptor table the job uses
+    auto stage_tiles = [&](int job, int buf) {
         if constexpr (T::kFrame) {
-            uint32_t tx = 0;
-            unsigned tma_mask = 0;
-#pragma unroll
-            for (int q = 0; q < NW * 2; ++q) {
-                const int wi = q >> 1, frame = q & 1;
-                const int g = min(job * NW + wi, n_total - 1);
+            TileDesc* desc = reinterpret_cast<TileDesc*>(smem + S::TD_OFF) + buf * (NW * 2);
+            if (lane < NW * 2) {
+                const int q = lane, frame = q & 1;
+                const int g = min(job * NW + (q >> 1), n_total - 1);
                 const WinGeo w = window_geo(p, g);
-                int oy, ox;
-                float vy, vx;
-                frame_origin<LOADER>(p, g, w, frame, oy, ox, vy, vx);
-                const bool interior = p.use_tma && ox >= 0 && oy >= 0 && ox + T::USED <= p.Wf &&
-                                      oy + T::BY <= p.H;
-                int* tile_d = reinterpret_cast<int*>(smem + S::TD_OFF);
-                if (lane == 0) tile_d[q] = interior ? (ox & 15) : 0;
-                if (interior) {
+                TileDesc dsc;
+                frame_origin<LOADER>(p, g, w, frame, dsc.oy, dsc.ox, dsc.vy, dsc.vx);
+                const bool interior = p.use_tma && dsc.ox >= 0 && dsc.oy >= 0 &&
+                                      dsc.ox + T::USED <= p.Wf && dsc.oy + T::BY <= p.H;
+                dsc.pair = w.pair;
+                dsc.r0 = w.r0;
+                dsc.c0 = w.c0;
+                dsc.d = interior ? (dsc.ox & 15) : -1;
+                desc[q] = dsc;
+            }
+            __syncwarp();
+            uint32_t tx = 0;
+#pragma unroll 1
+            for (int q = 0; q < NW * 2; ++q) {
+                const TileDesc dsc = desc[q];
+                if (dsc.d >= 0) {
                     tx += T::TX;
-                    tma_mask |= 1u << q;
                 } else {
                     // border window: the reference addresses taps by FLAT index clamped to
                     // [0, H*W-1] (PB:172-180, 213-214), i.e. columns wrap into neighbouring rows.
-                    const unsigned char* f = (frame ? p.fb : p.fa) + w.pair * p.pair_stride;
+                    const unsigned char* f = ((q & 1) ? p.fb : p.fa) + dsc.pair * p.pair_stride;
                     unsigned char* tile = smem + S::TILE_OFF + q * T::BYTES;
                     const long long last = static_cast<long long>(p.H) * p.Wf - 1;
                     for (int e = lane; e < T::BY * T::USED; e += 32) {
                         const int i = e / T::USED, jj = e - i * T::USED;
-                        long long flat = static_cast<long long>(oy + i) * p.Wf + (ox + jj);
+                        long long flat = static_cast<long long>(dsc.oy + i) * p.Wf + (dsc.ox + jj);
                         flat = flat < 0 ? 0 : (flat > last ? last : flat);
                         const int yy = static_cast<int>(flat / p.Wf);
                         const int xx = static_cast<int>(flat - static_cast<long long>(yy) * p.Wf);
@@ -284,34 +311,37 @@ __global__ void __launch_bounds__(32) piv_fused_kernel(const __grid_constant__ C
                     }
                 }
             }
-            if (tma_mask != 0) {
+            if (tx != 0) {
                 if (lane == 0) {
                     fence_proxy_async();
                     mbar_arrive_expect_tx(bar, tx);
-#pragma unroll
+#pragma unroll 1
                     for (int q = 0; q < NW * 2; ++q) {
-                        if (tma_mask & (1u << q)) {
-                            const int wi = q >> 1, frame = q & 1;
-                            const int g = min(job * NW + wi, n_total - 1);
-                            const WinGeo w = window_geo(p, g);
-                            int oy, ox;
-                            float vy, vx;
-                            frame_origin<LOADER>(p, g, w, frame, oy, ox, vy, vx);
-                            tma_load_3d(smem_u32(smem + S::TILE_OFF + q * T::BYTES),
-                                        frame ? &tmB : &tmA, bar, ox & ~15, oy, w.pair);
-                        }
+                        const TileDesc dsc = desc[q];
+                        if (dsc.d >= 0)
+                            tma_load_3d(smem_u32(smem + S::TILE_OFF + q * T::BYTES), (q & 1) ? &tmB : &tmA,
+                                        bar, dsc.ox & ~15, dsc.oy, dsc.pair);
                     }
                 }
                 pending = true;
             }
             __syncwarp();
+            // gathered tiles are stored from byte 0
+            if (lane < NW * 2 && desc[lane].d < 0) desc[lane].d = 0;
+            __syncwarp();
         }
     };
 
-    int job = blockIdx.x;
-    if (job < njobs) stage_tiles(job);
+    // every warp of the CTA runs the same number of iterations (block barriers inside); a warp
+    // without work re-does the last job and suppresses its output (n_total guard via `active`)
+    int job = blockIdx.x * S::NWARPS + warp;
+    int buf = 0;
+    stage_tiles(min(job, njobs - 1), buf);
 
-    for (; job < njobs; job += gridDim.x) {
+    for (int base = blockIdx.x * S::NWARPS; base < njobs; base += job_stride, job += job_stride, buf ^= 1) {
+        const bool active = job < njobs;
+        const int job_c = min(job, njobs - 1);
+        __syncthreads();
         if constexpr (T::kFrame) {
             if (pending) {
                 mbar_wait(bar, parity);
@@ -326,258 +356,246 @@ __global__ void __launch_bounds__(32) piv_fused_kernel(const __grid_constant__ C
             float2* xw = reinterpret_cast<float2*>(smem + S::XW_OFF);
             int* xf = reinterpret_cast<int*>(smem + S::XF_OFF);
             bool flag = false;
+            const TileDesc* desc = reinterpret_cast<const TileDesc*>(smem + S::TD_OFF) + buf * (NW * 2);
 #pragma unroll
             for (int e = lane; e < NW * 2 * W; e += 32) {
                 const int j = e & (W - 1), q = e >> LOGW;      // q = wi*2 + frame
-                const int g = min(job * NW + (q >> 1), n_total - 1);
-                const WinGeo w = window_geo(p, g);
-                int oy, ox;
-                float vy, vx;
-                frame_origin<LOADER>(p, g, w, q & 1, oy, ox, vy, vx);
-                const AxisTap cx = cws_axis(w.c0 + j, vx);
+                const TileDesc dsc = desc[q];
+                const AxisTap cx = cws_axis(dsc.c0 + j, dsc.vx);
                 xw[e] = make_float2(cx.w1, cx.w0);
-                xf[e] = (cx.exact ? 2 : 0) | ((cx.lo - (ox + j)) & 1);
+                xf[e] = (cx.exact ? 2 : 0) | ((cx.lo - (dsc.ox + j)) & 1);
                 flag |= cx.exact;
-                // rows: every row index appears as some j, W is square -> same loop covers them
-                const AxisTap cy = cws_axis(w.r0 + j, vy);
+                // rows: every row index appears as some j (square windows) -> same loop covers them
+                const AxisTap cy = cws_axis(dsc.r0 + j, dsc.vy);
                 flag |= cy.exact;
             }
             anyflag = __any_sync(FULL, flag);
             __syncwarp();
         }
 
-        // =============================== phase R ===========================================
+        // ===================================================================================
+        // Six FFT steps per lane around ONE shared transform body (the unrolled W-point FFT is the
+        // bulk of the code; sharing it keeps every phase's working set inside the instruction cache):
+        //   s = 0, 1  row FFTs of z = a + i b                  (phase R)  -> M
+        //   s = 2, 3  forward FFTs of the column pair (k, W-k) (phase C)
+        //   s = 4     inverse column FFT of the product        (phase C)  -> Q
+        //   s = 5     inverse FFT of two packed Hermitian rows (phase I)  -> map rows in registers
+        // ===================================================================================
+        const int wi = lane / HALF;            // window of this lane in phases C, I, E
+        const int kc = lane % HALF;            // column pair (kc, W-kc); kc == 0: columns 0 and W/2
+        const int l = kc;                      // rows l and l + W/2 in phase I
+        const int col1 = kc, col2 = kc ? W - kc : HALF;
+        float2* const Mw = reinterpret_cast<float2*>(smem + S::EX_OFF + wi * G::MB);
+        float sum_a = 0.f, sum_b = 0.f;        // pixel sums of the window (valid in lanes kc == 0)
+        float2 x[W];                           // the FFT operand
+        float2 xs[(W <= 32) ? W : 1];          // W <= 32: spectrum of column k kept while column W-k is transformed
+        constexpr int NSTEP = (SINK == SK_WIN) ? 2 : 6;
 #pragma unroll 1
-        for (int it = 0; it < 2; ++it) {
-            const int grow = lane + 32 * it;
-            const int wi = grow >> LOGW, t = grow & (W - 1);
-            const int g = min(job * NW + wi, n_total - 1);
-            float2 x[W];
-            if constexpr (LOADER == LD_FRAME_INT) {
-                const unsigned char* ta = smem + S::TILE_OFF + (wi * 2) * T::BYTES;
-                const unsigned char* tb = ta + T::BYTES;
-                const int* tile_d = reinterpret_cast<const int*>(smem + S::TD_OFF);
-                uint32_t wa[W / 4], wb[W / 4];
-                load_row_words<W, LOADER, W / 4>(ta, t, tile_d[wi * 2], wa);
-                load_row_words<W, LOADER, W / 4>(tb, t, tile_d[wi * 2 + 1], wb);
-                static_for<0, W>([&](auto jc) {
-                    constexpr int j = decltype(jc)::value;
-                    x[j] = make_float2(u8f(wa[j >> 2], j & 3), u8f(wb[j >> 2], j & 3));
-                });
-            } else if constexpr (LOADER == LD_FRAME_CWS) {
-                const WinGeo w = window_geo(p, g);
-                const float2* xw = reinterpret_cast<const float2*>(smem + S::XW_OFF);
-                const int* xf = reinterpret_cast<const int*>(smem + S::XF_OFF);
-                static_for<0, 2>([&](auto fc) {
-                    constexpr int frame = decltype(fc)::value;
-                    int oy, ox;
-                    float vy, vx;
-                    frame_origin<LOADER>(p, g, w, frame, oy, ox, vy, vx);
-                    const AxisTap cy = cws_axis(w.r0 + t, vy);
-                    const int jy = (cy.lo - (oy + t)) & 1;
-                    const unsigned char* tile = smem + S::TILE_OFF + (wi * 2 + frame) * T::BYTES;
-                    const int d = reinterpret_cast<const int*>(smem + S::TD_OFF)[wi * 2 + frame];
-                    uint32_t r0w[W / 4 + 1], r1w[W / 4 + 1];
-                    load_row_words<W, LOADER, W / 4 + 1>(tile, t, d, r0w);
-                    load_row_words<W, LOADER, W / 4 + 1>(tile, t + 1, d, r1w);
-                    const float2* xwq = xw + (wi * 2 + frame) * W;
-                    const int* xfq = xf + (wi * 2 + frame) * W;
-                    float l0 = u8f(r0w[0], 0), l1 = u8f(r1w[0], 0);
-                    if (!anyflag) {
-                        static_for<0, W>([&](auto jc) {
-                            constexpr int j = decltype(jc)::value;
-                            const float h0 = u8f(r0w[(j + 1) >> 2], (j + 1) & 3);
-                            const float h1 = u8f(r1w[(j + 1) >> 2], (j + 1) & 3);
-                            const float2 wx = xwq[j];
-                            // PB:187-192 evaluation order, no FMA contraction
-                            float acc = __fmul_rn(__fmul_rn(l0, wx.x), cy.w1);
-                            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(h0, wx.y), cy.w1));
-                            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(l1, wx.x), cy.w0));
-                            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(h1, wx.y), cy.w0));
-                            if constexpr (frame == 0) x[j].x = acc; else x[j].y = acc;
-                            l0 = h0; l1 = h1;
-                        });
-                    } else {
-                        static_for<0, W>([&](auto jc) {
-                            constexpr int j = decltype(jc)::value;
-                            const float h0 = u8f(r0w[(j + 1) >> 2], (j + 1) & 3);
-                            const float h1 = u8f(r1w[(j + 1) >> 2], (j + 1) & 3);
-                            const float2 wx = xwq[j];
-                            const int fl = xfq[j];
-                            float acc = __fmul_rn(__fmul_rn(l0, wx.x), cy.w1);
-                            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(h0, wx.y), cy.w1));
-                            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(l1, wx.x), cy.w0));
-                            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(h1, wx.y), cy.w0));
-                            // exact-integer coordinate on either axis: tap (floor y, floor x) (PB:170, 193)
-                            const float s0 = (fl & 1) ? h0 : l0, s1 = (fl & 1) ? h1 : l1;
-                            const float q11 = jy ? s1 : s0;
-                            acc = ((fl & 2) || cy.exact) ? q11 : acc;
-                            if constexpr (frame == 0) x[j].x = acc; else x[j].y = acc;
-                            l0 = h0; l1 = h1;
-                        });
-                    }
-                });
-            } else if constexpr (LOADER == LD_EXPL_F32) {
-                const float4* ra = reinterpret_cast<const float4*>(
-                    static_cast<const float*>(p.wa) + (static_cast<long long>(g) * W + t) * W);
-                const float4* rb = reinterpret_cast<const float4*>(
-                    static_cast<const float*>(p.wb) + (static_cast<long long>(g) * W + t) * W);
-                static_for<0, W / 4>([&](auto cc) {
-                    constexpr int c = decltype(cc)::value;
-                    const float4 va = __ldg(ra + c), vb = __ldg(rb + c);
-                    x[4 * c] = make_float2(va.x, vb.x);
-                    x[4 * c + 1] = make_float2(va.y, vb.y);
-                    x[4 * c + 2] = make_float2(va.z, vb.z);
-                    x[4 * c + 3] = make_float2(va.w, vb.w);
-                });
-            } else {
-                const uint4* ra = reinterpret_cast<const uint4*>(
-                    static_cast<const unsigned char*>(p.wa) + (static_cast<long long>(g) * W + t) * W);
-                const uint4* rb = reinterpret_cast<const uint4*>(
-                    static_cast<const unsigned char*>(p.wb) + (static_cast<long long>(g) * W + t) * W);
-                static_for<0, W / 16>([&](auto cc) {
-                    constexpr int c = decltype(cc)::value;
-                    const uint4 qa = __ldg(ra + c), qb = __ldg(rb + c);
-                    const uint32_t wa[4] = {qa.x, qa.y, qa.z, qa.w};
-                    const uint32_t wb[4] = {qb.x, qb.y, qb.z, qb.w};
-                    static_for<0, 16>([&](auto bc) {
-                        constexpr int b = decltype(bc)::value;
-                        x[16 * c + b] = make_float2(u8f(wa[b >> 2], b & 3), u8f(wb[b >> 2], b & 3));
+        for (int s = 0; s < NSTEP; ++s) {
+            if (s == 2 || s == 4 || s == 5) __syncthreads();   // lock step: shared instruction fetch
+            // ---------------------------------------------------------------- load
+            const int grow = lane + 32 * s;
+            const int rwi = (grow >> LOGW) & (NW - 1), rt = grow & (W - 1);     // row mapping (s < 2)
+            const int g = min(job_c * NW + rwi, n_total - 1);
+            if (s < 2) {
+                if constexpr (LOADER == LD_FRAME_INT) {
+                    const unsigned char* ta = smem + S::TILE_OFF + (rwi * 2) * T::BYTES;
+                    const unsigned char* tb = ta + T::BYTES;
+                    const TileDesc* desc = reinterpret_cast<const TileDesc*>(smem + S::TD_OFF) + buf * (NW * 2);
+                    uint32_t wa[W / 4], wb[W / 4];
+                    load_row_words<W, LOADER, W / 4>(ta, rt, desc[rwi * 2].d, wa);
+                    load_row_words<W, LOADER, W / 4>(tb, rt, desc[rwi * 2 + 1].d, wb);
+                    static_for<0, W>([&](auto jc) {
+                        constexpr int j = decltype(jc)::value;
+                        x[j] = make_float2(u8f(wa[j >> 2], j & 3), u8f(wb[j >> 2], j & 3));
                     });
+                } else if constexpr (LOADER == LD_FRAME_CWS) {
+                    const TileDesc* desc = reinterpret_cast<const TileDesc*>(smem + S::TD_OFF) + buf * (NW * 2);
+                    const float2* xw = reinterpret_cast<const float2*>(smem + S::XW_OFF);
+                    const int* xf = reinterpret_cast<const int*>(smem + S::XF_OFF);
+                    static_for<0, 2>([&](auto fc) {
+                        constexpr int frame = decltype(fc)::value;
+                        const TileDesc dsc = desc[rwi * 2 + frame];
+                        const AxisTap cy = cws_axis(dsc.r0 + rt, dsc.vy);
+                        const int jy = (cy.lo - (dsc.oy + rt)) & 1;
+                        const unsigned char* tile = smem + S::TILE_OFF + (rwi * 2 + frame) * T::BYTES;
+                        const int d = dsc.d;
+                        uint32_t r0w[W / 4 + 1], r1w[W / 4 + 1];
+                        load_row_words<W, LOADER, W / 4 + 1>(tile, rt, d, r0w);
+                        load_row_words<W, LOADER, W / 4 + 1>(tile, rt + 1, d, r1w);
+                        const float2* xwq = xw + (rwi * 2 + frame) * W;
+                        const int* xfq = xf + (rwi * 2 + frame) * W;
+                        float l0 = u8f(r0w[0], 0), l1 = u8f(r1w[0], 0);
+                        if (!anyflag) {
+                            static_for<0, W>([&](auto jc) {
+                                constexpr int j = decltype(jc)::value;
+                                const float h0 = u8f(r0w[(j + 1) >> 2], (j + 1) & 3);
+                                const float h1 = u8f(r1w[(j + 1) >> 2], (j + 1) & 3);
+                                const float2 wx = xwq[j];
+                                // PB:187-192 evaluation order, no FMA contraction
+                                float acc = __fmul_rn(__fmul_rn(l0, wx.x), cy.w1);
+                                acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(h0, wx.y), cy.w1));
+                                acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(l1, wx.x), cy.w0));
+                                acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(h1, wx.y), cy.w0));
+                                if constexpr (frame == 0) x[j].x = acc; else x[j].y = acc;
+                                l0 = h0; l1 = h1;
+                            });
+                        } else {
+                            static_for<0, W>([&](auto jc) {
+                                constexpr int j = decltype(jc)::value;
+                                const float h0 = u8f(r0w[(j + 1) >> 2], (j + 1) & 3);
+                                const float h1 = u8f(r1w[(j + 1) >> 2], (j + 1) & 3);
+                                const float2 wx = xwq[j];
+                                const int fl = xfq[j];
+                                float acc = __fmul_rn(__fmul_rn(l0, wx.x), cy.w1);
+                                acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(h0, wx.y), cy.w1));
+                                acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(l1, wx.x), cy.w0));
+                                acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(h1, wx.y), cy.w0));
+                                // exact-integer coordinate on either axis: tap (floor y, floor x) (PB:170, 193)
+                                const float s0 = (fl & 1) ? h0 : l0, s1 = (fl & 1) ? h1 : l1;
+                                const float q11 = jy ? s1 : s0;
+                                acc = ((fl & 2) || cy.exact) ? q11 : acc;
+                                if constexpr (frame == 0) x[j].x = acc; else x[j].y = acc;
+                                l0 = h0; l1 = h1;
+                            });
+                        }
+                    });
+                } else if constexpr (LOADER == LD_EXPL_F32) {
+                    const float4* ra = reinterpret_cast<const float4*>(
+                        static_cast<const float*>(p.wa) + (static_cast<long long>(g) * W + rt) * W);
+                    const float4* rb = reinterpret_cast<const float4*>(
+                        static_cast<const float*>(p.wb) + (static_cast<long long>(g) * W + rt) * W);
+                    static_for<0, W / 4>([&](auto cc) {
+                        constexpr int c = decltype(cc)::value;
+                        const float4 va = __ldg(ra + c), vb = __ldg(rb + c);
+                        x[4 * c] = make_float2(va.x, vb.x);
+                        x[4 * c + 1] = make_float2(va.y, vb.y);
+                        x[4 * c + 2] = make_float2(va.z, vb.z);
+                        x[4 * c + 3] = make_float2(va.w, vb.w);
+                    });
+                } else {
+                    const uint4* ra = reinterpret_cast<const uint4*>(
+                        static_cast<const unsigned char*>(p.wa) + (static_cast<long long>(g) * W + rt) * W);
+                    const uint4* rb = reinterpret_cast<const uint4*>(
+                        static_cast<const unsigned char*>(p.wb) + (static_cast<long long>(g) * W + rt) * W);
+                    static_for<0, W / 16>([&](auto cc) {
+                        constexpr int c = decltype(cc)::value;
+                        const uint4 qa = __ldg(ra + c), qb = __ldg(rb + c);
+                        const uint32_t wa[4] = {qa.x, qa.y, qa.z, qa.w};
+                        const uint32_t wb[4] = {qb.x, qb.y, qb.z, qb.w};
+                        static_for<0, 16>([&](auto bc) {
+                            constexpr int b = decltype(bc)::value;
+                            x[16 * c + b] = make_float2(u8f(wa[b >> 2], b & 3), u8f(wb[b >> 2], b & 3));
+                        });
+                    });
+                }
+
+            } else if (s == 2) {
+                static_for<0, W>([&](auto tc) { constexpr int t = decltype(tc)::value; x[t] = Mw[t * PM + col1]; });
+            } else if (s == 3) {
+                static_for<0, W>([&](auto tc) { constexpr int t = decltype(tc)::value; x[t] = Mw[t * PM + col2]; });
+            } else if (s == 5) {
+                // two Hermitian rows l, l + W/2 of Q packed into one complex inverse FFT
+                const float2* Qw = Mw;
+                const float2 a0 = Qw[l * PQ], b0 = Qw[(l + HALF) * PQ];
+                x[0] = make_float2(b0.x, a0.x);
+                x[HALF] = make_float2(b0.y, a0.y);
+                static_for<1, HALF>([&](auto kc_) {
+                    constexpr int k = decltype(kc_)::value;
+                    const float2 R1 = Qw[l * PQ + k], R2 = Qw[(l + HALF) * PQ + k];
+                    x[k] = make_float2(R1.y + R2.x, R1.x - R2.y);
+                    x[W - k] = make_float2(R2.x - R1.y, R1.x + R2.y);
                 });
+                __syncwarp();                   // Q fully read before the map overwrites it
             }
 
             if constexpr (SINK == SK_WIN) {
-                if (job * NW + wi < n_total) {
-                    float4* oa = reinterpret_cast<float4*>(p.win_a_out + (static_cast<long long>(g) * W + t) * W);
-                    float4* ob = reinterpret_cast<float4*>(p.win_b_out + (static_cast<long long>(g) * W + t) * W);
+                if (active && job_c * NW + rwi < n_total) {
+                    float4* oa = reinterpret_cast<float4*>(p.win_a_out + (static_cast<long long>(g) * W + rt) * W);
+                    float4* ob = reinterpret_cast<float4*>(p.win_b_out + (static_cast<long long>(g) * W + rt) * W);
                     static_for<0, W / 4>([&](auto cc) {
                         constexpr int c = decltype(cc)::value;
                         oa[c] = make_float4(x[4 * c].x, x[4 * c + 1].x, x[4 * c + 2].x, x[4 * c + 3].x);
                         ob[c] = make_float4(x[4 * c].y, x[4 * c + 1].y, x[4 * c + 2].y, x[4 * c + 3].y);
                     });
                 }
-            } else {
-                F::run(x);
-                float2* Mrow = reinterpret_cast<float2*>(smem + S::EX_OFF + wi * G::MB) + t * PM;
+                continue;
+            }
+
+            F::run(x);
+
+            // ---------------------------------------------------------------- store
+            if (s < 2) {
+                float2* Mrow = reinterpret_cast<float2*>(smem + S::EX_OFF + rwi * G::MB) + rt * PM;
                 static_for<0, W>([&](auto kc_) {
                     constexpr int k = decltype(kc_)::value;
                     Mrow[k] = x[F::pos(k)];
                 });
-            }
-        }
-        __syncwarp();
-
-        // tiles are consumed: request the next job's while this one is transformed
-        {
-            const int next = job + gridDim.x;
-            if (next < njobs) stage_tiles(next);
-        }
-        if constexpr (SINK == SK_WIN) continue;
-
-        // =============================== phase C ===========================================
-        const int wi = lane / HALF;            // window of this lane in phases C, I, E
-        const int kc = lane % HALF;            // column pair (kc, W-kc); kc == 0: columns 0 and W/2
-        float sum_a = 0.f, sum_b = 0.f;        // pixel sums of the window (valid in lanes kc == 0)
-        {
-            float2* Mw = reinterpret_cast<float2*>(smem + S::EX_OFF + wi * G::MB);
-            const int col1 = kc, col2 = kc ? W - kc : HALF;
-            float2 pq[W];                      // inverse-FFT input, (im, re) swapped
-            if constexpr (W <= 32) {
-                float2 X[W], Y[W];
-                static_for<0, W>([&](auto tc) { constexpr int t = decltype(tc)::value; X[t] = Mw[t * PM + col1]; });
-                F::run(X);
-                static_for<0, W>([&](auto tc) { constexpr int t = decltype(tc)::value; Y[t] = Mw[t * PM + col2]; });
-                F::run(Y);
-                __syncwarp();                  // M fully read before Q overwrites it
+                if (s == 1) {
+                    __syncwarp();
+                    // tiles are consumed: request the next job's while this one is transformed
+                    if (base + job_stride < njobs) stage_tiles(min(job + job_stride, njobs - 1), buf ^ 1);
+                }
+            } else if (s == 2) {
+                if constexpr (W <= 32) {
+                    static_for<0, W>([&](auto ic) { constexpr int i = decltype(ic)::value; xs[i] = x[i]; });
+                } else {
+                    // W == 64: two 64-point spectra do not fit in registers; X is parked in its own
+                    // (lane-private) column of M, natural order, and streamed back during the product
+                    static_for<0, W>([&](auto rc) { constexpr int r = decltype(rc)::value; Mw[r * PM + col1] = x[F::pos(r)]; });
+                }
+            } else if (s == 3) {
+                // x = spectrum Y of column W-k; X = spectrum of column k.  Product, (im, re) swapped
+                // for the inverse transform, written back into x.
+                auto Xn = [&](auto rc) -> float2 {
+                    constexpr int r = decltype(rc)::value;
+                    if constexpr (W <= 32) return xs[F::pos(r)];
+                    else return Mw[r * PM + col1];
+                };
+                float2 pq[W];
                 if (kc != 0) {
                     static_for<0, W>([&](auto rc) {
                         constexpr int r = decltype(rc)::value;
-                        const float2 P = xcorr_bin(X[F::pos(r)], Y[F::pos((W - r) % W)]);
+                        const float2 P = xcorr_bin(Xn(rc), x[F::pos((W - r) % W)]);
                         pq[r] = make_float2(P.y, P.x);
                     });
                 } else {
-                    sum_a = X[F::pos(0)].x;
-                    sum_b = X[F::pos(0)].y;
-                    static_for<0, HALF + 1>([&](auto rc) {
-                        constexpr int r = decltype(rc)::value;
-                        constexpr int nr = (W - r) % W;
-                        float2 P0 = xcorr_bin(X[F::pos(r)], X[F::pos(nr)]);
-                        const float2 Ph = xcorr_bin(Y[F::pos(r)], Y[F::pos(nr)]);
-                        if constexpr (r == 0 && SINK == SK_DISP) P0 = make_float2(0.f, 0.f);   // drop the DC bin (mean product): a constant, removed by `- amin` anyway
-                        // out[r] = P0 + i Ph ; out[-r] = conj(P0) + i conj(Ph); stored (im, re)
-                        pq[r] = make_float2(P0.y + Ph.x, P0.x - Ph.y);
-                        if constexpr (nr != r) pq[nr] = make_float2(Ph.x - P0.y, P0.x + Ph.y);
-                    });
-                }
-            } else {
-                // W == 64: two 64-point spectra do not fit in registers; X is parked in its own
-                // (lane-private) column of M and streamed back during the product.
-                float2 Y[W];
-                {
-                    float2 X[W];
-                    static_for<0, W>([&](auto tc) { constexpr int t = decltype(tc)::value; X[t] = Mw[t * PM + col1]; });
-                    F::run(X);
-                    static_for<0, W>([&](auto rc) { constexpr int r = decltype(rc)::value; Mw[r * PM + col1] = X[F::pos(r)]; });
-                }
-                static_for<0, W>([&](auto tc) { constexpr int t = decltype(tc)::value; Y[t] = Mw[t * PM + col2]; });
-                F::run(Y);
-                if (kc != 0) {
-                    static_for<0, W>([&](auto rc) {
-                        constexpr int r = decltype(rc)::value;
-                        const float2 P = xcorr_bin(Mw[r * PM + col1], Y[F::pos((W - r) % W)]);
-                        pq[r] = make_float2(P.y, P.x);
-                    });
-                } else {
-                    const float2 dc = Mw[col1];
+                    const float2 dc = Xn(std::integral_constant<int, 0>{});
                     sum_a = dc.x;
                     sum_b = dc.y;
                     static_for<0, HALF + 1>([&](auto rc) {
                         constexpr int r = decltype(rc)::value;
                         constexpr int nr = (W - r) % W;
-                        float2 P0 = xcorr_bin(Mw[r * PM + col1], Mw[nr * PM + col1]);
-                        const float2 Ph = xcorr_bin(Y[F::pos(r)], Y[F::pos(nr)]);
+                        float2 P0 = xcorr_bin(Xn(rc), Xn(std::integral_constant<int, nr>{}));
+                        const float2 Ph = xcorr_bin(x[F::pos(r)], x[F::pos(nr)]);
+                        // drop the DC bin (mean product): a constant that `- amin` removes anyway
                         if constexpr (r == 0 && SINK == SK_DISP) P0 = make_float2(0.f, 0.f);
+                        // out[r] = P0 + i Ph ; out[-r] = conj(P0) + i conj(Ph); stored (im, re)
                         pq[r] = make_float2(P0.y + Ph.x, P0.x - Ph.y);
                         if constexpr (nr != r) pq[nr] = make_float2(Ph.x - P0.y, P0.x + Ph.y);
                     });
                 }
+                static_for<0, W>([&](auto ic) { constexpr int i = decltype(ic)::value; x[i] = pq[i]; });
+            } else if (s == 4) {
+                __syncwarp();                  // M (and the parked X) fully read before Q overwrites it
+                float2* Qw = Mw;
+                static_for<0, W>([&](auto tc) {
+                    constexpr int t = decltype(tc)::value;
+                    const float2 o = x[F::pos(t)];
+                    Qw[t * PQ + kc] = make_float2(o.y, o.x);
+                });
                 __syncwarp();
             }
-            F::run(pq);
-            float2* Qw = Mw;
-            static_for<0, W>([&](auto tc) {
-                constexpr int t = decltype(tc)::value;
-                const float2 o = pq[F::pos(t)];
-                Qw[t * PQ + kc] = make_float2(o.y, o.x);
-            });
         }
-        __syncwarp();
+        if constexpr (SINK == SK_WIN) continue;
 
-        // =============================== phase I ===========================================
-        const int l = kc;                       // rows l and l + W/2 of window wi
-        float2 y[W];
-        {
-            const float2* Qw = reinterpret_cast<const float2*>(smem + S::EX_OFF + wi * G::MB);
-            const float2 a0 = Qw[l * PQ], b0 = Qw[(l + HALF) * PQ];
-            y[0] = make_float2(b0.x, a0.x);
-            y[HALF] = make_float2(b0.y, a0.y);
-            static_for<1, HALF>([&](auto kc_) {
-                constexpr int k = decltype(kc_)::value;
-                const float2 R1 = Qw[l * PQ + k], R2 = Qw[(l + HALF) * PQ + k];
-                y[k] = make_float2(R1.y + R2.x, R1.x - R2.y);
-                y[W - k] = make_float2(R2.x - R1.y, R1.x + R2.y);
-            });
-        }
-        __syncwarp();                           // Q fully read before the map overwrites it
-        F::run(y);
-        // raw row l -> shifted row l + W/2 (values y[].y); raw row l + W/2 -> shifted row l (y[].x)
+        // raw row l -> shifted row l + W/2 (values x[].y); raw row l + W/2 -> shifted row l (x[].x)
         float* mapw = reinterpret_cast<float*>(smem + S::EX_OFF + wi * G::MB);
         float mx_hi = -FLT_MAX, mx_lo = -FLT_MAX, mn = FLT_MAX;     // hi: shifted row l + HALF
         static_for<0, W>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
             constexpr int sc = (j + HALF) % W;
-            const float2 o = y[F::pos(j)];
+            const float2 o = x[F::pos(j)];
             mapw[(l + HALF) * PC + sc] = o.y;
             mapw[l * PC + sc] = o.x;
             mx_hi = fmaxf(mx_hi, o.y);
@@ -589,8 +607,8 @@ __global__ void __launch_bounds__(32) piv_fused_kernel(const __grid_constant__ C
         if constexpr (SINK == SK_CORR) {
 #pragma unroll 1
             for (int w2 = 0; w2 < NW; ++w2) {
-                const int g = job * NW + w2;
-                if (g >= n_total) break;
+                const int g = job_c * NW + w2;
+                if (!active || g >= n_total) break;
                 const float* mw = reinterpret_cast<const float*>(smem + S::EX_OFF + w2 * G::MB);
                 float* out = p.corr_out + static_cast<long long>(g) * W * W;
                 for (int e = lane; e < W * W; e += 32)
@@ -679,8 +697,8 @@ __global__ void __launch_bounds__(32) piv_fused_kernel(const __grid_constant__ C
                 invalid = false;
                 ratio = 0.f;
             }
-            const int g = job * NW + wi;
-            if (l == 0 && g < n_total) {
+            const int g = job_c * NW + wi;
+            if (active && l == 0 && g < n_total) {
                 double uo = du + (p.base_u ? p.base_u[g] : 0.0);
                 double vo = dv + (p.base_v ? p.base_v[g] : 0.0);
                 if (p.pred_u) {
