@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cstdlib>
 
 #include "piv_params.h"
 
@@ -26,8 +27,14 @@ void count_launch();
 namespace pivb200 {
 
 template <int W, int LOADER, int SINK>
-static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const PassParams& p,
+static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const PassParams& p_in,
                       cudaStream_t stream) {
+    PassParams p = p_in;
+    {
+        // lock-step barriers (see piv_fused.cuh); PIVB200_SYNC_MASK overrides for experiments
+        static const int env_mask = [] { const char* e = getenv("PIVB200_SYNC_MASK"); return e ? atoi(e) : -1; }();
+        p.sync_mask = env_mask >= 0 ? env_mask : (1 << 2);      // measured best on B200: one barrier per job
+    }
     using S = Smem<W, LOADER>;
     auto kern = piv_fused_kernel<W, LOADER, SINK>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::CTA_BYTES);

@@ -300,13 +300,24 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                     // [0, H*W-1] (PB:172-180, 213-214), i.e. columns wrap into neighbouring rows.
                     const unsigned char* f = ((q & 1) ? p.fb : p.fa) + dsc.pair * p.pair_stride;
                     unsigned char* tile = smem + S::TILE_OFF + q * T::BYTES;
-                    const long long last = static_cast<long long>(p.H) * p.Wf - 1;
+                    const int last_y = p.H - 1, last_x = p.Wf - 1;
+#pragma unroll 4
                     for (int e = lane; e < T::BY * T::USED; e += 32) {
                         const int i = e / T::USED, jj = e - i * T::USED;
-                        long long flat = static_cast<long long>(dsc.oy + i) * p.Wf + (dsc.ox + jj);
-                        flat = flat < 0 ? 0 : (flat > last ? last : flat);
-                        const int yy = static_cast<int>(flat / p.Wf);
-                        const int xx = static_cast<int>(flat - static_cast<long long>(yy) * p.Wf);
+                        int yy = dsc.oy + i, xx = dsc.ox + jj;
+                        if (xx < 0 || xx > last_x) {
+                            // column outside the frame: the flat index wraps into a neighbouring row
+                            long long flat = static_cast<long long>(yy) * p.Wf + xx;
+                            const long long last = static_cast<long long>(p.H) * p.Wf - 1;
+                            flat = flat < 0 ? 0 : (flat > last ? last : flat);
+                            const unsigned uf = static_cast<unsigned>(flat);      // H * W < 2^31 (checked on the host)
+                            yy = static_cast<int>(uf / static_cast<unsigned>(p.Wf));
+                            xx = static_cast<int>(uf - static_cast<unsigned>(yy) * static_cast<unsigned>(p.Wf));
+                        } else if (yy < 0) {
+                            yy = 0; xx = 0;                 // flat < 0 clamps to the first pixel
+                        } else if (yy > last_y) {
+                            yy = last_y; xx = last_x;       // flat > H*W-1 clamps to the last pixel
+                        }
                         tile[T::off(i, jj >> 4) + (jj & 15)] = f[static_cast<long long>(yy) * p.pitch + xx];
                     }
                 }
@@ -341,7 +352,7 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
     for (int base = blockIdx.x * S::NWARPS; base < njobs; base += job_stride, job += job_stride, buf ^= 1) {
         const bool active = job < njobs;
         const int job_c = min(job, njobs - 1);
-        __syncthreads();
+        if (p.sync_mask & 64) __syncthreads();
         if constexpr (T::kFrame) {
             if (pending) {
                 mbar_wait(bar, parity);
@@ -392,7 +403,7 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
         constexpr int NSTEP = (SINK == SK_WIN) ? 2 : 6;
 #pragma unroll 1
         for (int s = 0; s < NSTEP; ++s) {
-            if (s == 2 || s == 4 || s == 5) __syncthreads();   // lock step: shared instruction fetch
+            if ((p.sync_mask >> s) & 1) __syncthreads();        // lock step: shared instruction fetch
             // ---------------------------------------------------------------- load
             const int grow = lane + 32 * s;
             const int rwi = (grow >> LOGW) & (NW - 1), rt = grow & (W - 1);     // row mapping (s < 2)

@@ -77,6 +77,7 @@ static int check_geometry(int H, int W, int pitch, int wind, int overlap, int n_
     *n_rows = (H - wind) / (wind - overlap) + 1;
     *n_cols = (W - wind) / (wind - overlap) + 1;
     if (static_cast<long long>(*n_rows) * *n_cols * n_pairs >= (1ll << 30)) return PIVB200_E_SIZE;
+    if (static_cast<long long>(H) * W >= (1ll << 31)) return PIVB200_E_SIZE;
     return 0;
 }
 
