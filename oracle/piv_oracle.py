@@ -206,8 +206,12 @@ def correlation_to_displacement(corr: np.ndarray, n_rows: int, n_cols: int,
 # --------------------------------------------------------------------------------------
 def extended_search_area_piv(frame_a: np.ndarray, frame_b: np.ndarray, window_size: int = 32,
                              overlap: int = 0, validate: bool = False,
-                             validation_ratio: float = 1.2, workers: int = -1):
-    """PB:459-520 (first pass, float64 after the mean normalisation)."""
+                             validation_ratio: float = 1.2, workers: int = -1,
+                             compute_dtype=np.float64, stash: dict = None):
+    """PB:459-520 (first pass, float64 after the mean normalisation).  ``stash`` (test hook, not
+    reference behaviour) receives a copy of the min-subtracted correlation maps under "corr".  ``compute_dtype=float32``
+    is NOT the reference: it re-evaluates the same maths in single precision so that tests can
+    tell ill-conditioned vectors (those that move when the arithmetic changes) from real errors."""
     if overlap >= window_size:
         raise ValueError("Overlap has to be smaller than the window_size")
     if window_size > frame_a.shape[-2] or window_size > frame_a.shape[-1]:
@@ -219,8 +223,12 @@ def extended_search_area_piv(frame_a: np.ndarray, frame_b: np.ndarray, window_si
     with np.errstate(all="ignore"):
         aa = aa / aa.mean(axis=(-2, -1), dtype=np.float64, keepdims=True)
         bb = bb / bb.mean(axis=(-2, -1), dtype=np.float64, keepdims=True)
+    if compute_dtype != np.float64:
+        aa, bb = aa.astype(compute_dtype), bb.astype(compute_dtype)
     corr = correlate_fft(aa, bb, workers=workers)
     corr = corr - corr.min(axis=(-2, -1), keepdims=True)
+    if stash is not None:
+        stash["corr"] = corr.copy()
     u, v, mask = correlation_to_displacement(corr, n_rows, n_cols, validate, validation_ratio)
     return u, v, x, y, mask
 
@@ -236,7 +244,9 @@ class PivIteration:
 
     mode = "CWS"
 
-    def __init__(self, frame_shape, wind_size, overlap, workers: int = -1):
+    def __init__(self, frame_shape, wind_size, overlap, workers: int = -1, compute_dtype=None):
+        # compute_dtype=float64 is NOT the reference (which correlates in float32): conditioning probe
+        self.compute_dtype = compute_dtype
         self.frame_shape = tuple(frame_shape)
         self.wind_size, self.overlap = wind_size, overlap
         self.n_rows, self.n_cols = get_field_shape(frame_shape, wind_size, overlap)
@@ -255,8 +265,11 @@ class PivIteration:
         if validation_mask is not None:
             val_pred = resample_predictor(x0, y0, validation_mask, self.slice_y, self.slice_x) >= .5
         aa, bb, u_base, v_base, u0, v0 = self.shifted_windows(frame_a, frame_b, u0, v0, val_pred)
+        if self.compute_dtype is not None:
+            aa, bb = aa.astype(self.compute_dtype), bb.astype(self.compute_dtype)
         corr = correlate_fft(aa, bb, workers=self.workers)
         corr = corr - corr.min(axis=(-2, -1), keepdims=True)
+        self.last_corr = corr.copy()            # test hook (conditioning analysis), not reference behaviour
         du, dv, val = correlation_to_displacement(corr, self.n_rows, self.n_cols,
                                                   validation_mask is not None)
         u = u_base + du

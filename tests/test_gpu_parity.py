@@ -1,0 +1,442 @@
+"""GPU parity tests: the sm_100a path (called through the C ABI of libpivb200.so) against the CPU
+oracle on the same seeded inputs and against the golden vectors of the unmodified reference.
+
+Tolerances (BASELINE.json north_star):
+  * integer / byte work (window extraction, DWS shift, CWS bilinear taps): BIT-EXACT;
+  * validation masks and integer peaks: identical, except documented ill-conditioned windows;
+  * sub-pixel displacements: within 1e-3 px of the reference (TOL_PX), in practice ~1e-6.
+
+"Ill-conditioned" is decided from the ORACLE's correlation map, never from the kernel's output:
+a vector is ill-conditioned when a relative perturbation of 1e-6 of the peak height (a few
+float32 ulps of the map) moves the 3-point log fit by more than COND_PX, when the two largest
+map values tie within 1e-5, or when the peak ratio sits within 1e-4 of the 1.2 threshold --
+featureless / noise-only windows where rounding picks the peak, flat peaks next to the map
+minimum.  Those vectors are excluded from the tight comparison and their share is bounded
+(MAX_ILL); everything else must meet the north-star tolerance."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import piv_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_PX = 1e-3       # north-star tolerance on sub-pixel displacements
+COND_PX = 2e-4      # fit sensitivity (px) to a 1e-6 relative perturbation of the map above which a vector is ill-conditioned
+MAX_ILL = 0.12      # bound on the ill-conditioned share of a field (they sit in the noise / blank patches)
+MAX_ILL_VALID = 0.01  # ... and among the vectors the reference itself calls valid
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_util
+    return gpu_util
+
+
+@pytest.fixture(scope="module")
+def T():
+    import torchpiv_b200
+    return torchpiv_b200
+
+
+def conditioning(corr, val_ratio=1.2, rel=1e-6):
+    """corr: the oracle's min-subtracted maps [n, d, k].  Returns the well-conditioned flag [n]."""
+    c = corr.astype(np.float64).reshape(corr.shape[0], -1) + 1e-7
+    n, n2 = c.shape
+    k = corr.shape[2]
+    rows = np.arange(n)
+    m = c.argmax(axis=1)
+    cm = c[rows, m]
+
+    def nb(idx, bad):
+        return c[rows, np.where(bad, m, idx)]
+    cl, cr = nb(m + 1, m + 1 >= n2 - 1), nb(m - 1, m - 1 <= 0)
+    ct, cb = nb(m + k, m + k >= n2 - 1), nb(m - k, m - k <= 0)
+
+    def fit(lo, mid, hi):
+        with np.errstate(all="ignore"):
+            a, b_, e = np.log(lo), np.log(mid), np.log(hi)
+            return np.nan_to_num((a - e) / (2 * (e + a) - 4 * b_))
+    delta = rel * cm
+    sens = np.zeros(n)
+    for (lo, hi) in ((cr, cl), (cb, ct)):
+        base = fit(lo, cm, hi)
+        for s1 in (-1, 1):
+            for s2 in (-1, 1):
+                for s3 in (-1, 1):
+                    with np.errstate(all="ignore"):
+                        pert = fit(np.maximum(lo + s1 * delta, 1e-300), cm + s3 * delta,
+                                   np.maximum(hi + s2 * delta, 1e-300))
+                    sens = np.maximum(sens, np.abs(pert - base))
+    top2 = np.partition(c, -2, axis=1)[:, -2:]
+    tie = (top2[:, 1] - top2[:, 0]) <= 1e-5 * top2[:, 1]
+    flat = c.copy()
+    second = flat[rows, O.peak2peak_secondpeak(flat, m, k, 3)]
+    with np.errstate(all="ignore"):
+        ratio = cm / second
+    border = np.abs(ratio - val_ratio) < 1e-4 * val_ratio
+    return (sens < COND_PX) & ~tie & ~border
+
+
+def check_field(got_u, got_v, got_m, ref_u, ref_v, ref_m, corr, tight=2e-5):
+    """got = CUDA path, ref = reference (golden / oracle), corr = the oracle's maps (conditioning)."""
+    well = conditioning(corr).reshape(ref_u.shape)
+    assert 1.0 - well.mean() <= MAX_ILL, f"too many ill-conditioned vectors: {1 - well.mean():.3f}"
+    if ref_m is not None:
+        assert (~well & ~ref_m).sum() <= MAX_ILL_VALID * max(1, (~ref_m).sum())
+        assert np.array_equal(got_m[well], ref_m[well]), "validation mask differs on well-conditioned vectors"
+        assert (got_m != ref_m).mean() <= 0.01
+    eu, ev = np.abs(got_u - ref_u)[well], np.abs(got_v - ref_v)[well]
+    assert eu.max() < TOL_PX and ev.max() < TOL_PX, (eu.max(), ev.max())
+    # and the bulk is far tighter than the tolerance
+    assert np.quantile(eu, 0.99) < tight and np.quantile(ev, 0.99) < tight
+
+
+# ------------------------------------------------------------------------------------------
+# window extraction / shifting: bit-exact
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w,o", cases.PASS1_GEOMS + [(16, 12), (64, 60)])
+def test_windows_unshifted_bit_exact(G, w, o):
+    a, b = cases.small_pair(seed=1)
+    wa, wb = G.windows(a, b, w, o)
+    assert np.array_equal(wa, O.moving_window_array(a, w, o).astype(np.float32))
+    assert np.array_equal(wb, O.moving_window_array(b, w, o).astype(np.float32))
+
+
+@pytest.mark.parametrize("w,o", [(32, 16), (16, 8), (64, 32)])
+def test_windows_shifted_bit_exact(G, golden, w, o):
+    """TMA tiles + in-register realignment + border gathers vs the reference's flat-index
+    arithmetic: out-of-frame shifts, exact integers, one ulp below an integer."""
+    g = golden("shift.npz")
+    fr, vx, vy = cases.shift_case(seed=w, w=w, ovl=o)
+    idx = O.window_index_grid(fr.shape, w, o)
+    wa, wb = G.windows(fr, fr, w, o, "CWS", vx, vy)
+    assert np.array_equal(wa, O.bilinear_interpolation_cws(fr, idx, -vx[:, None, None], -vy[:, None, None]))
+    assert np.array_equal(wb, O.bilinear_interpolation_cws(fr, idx, vx[:, None, None], vy[:, None, None]))
+    assert cases.sha(wb) == str(g[f"cws_{w}_sha"])          # the reference's own output
+    ix, iy = np.rint(vx).astype(np.int64), np.rint(vy).astype(np.int64)
+    wa, wb = G.windows(fr, fr, w, o, "DWS", ix, iy)
+    assert np.array_equal(wa, O.interpolation_dws(fr, idx, -ix[:, None, None], -iy[:, None, None]).astype(np.float32))
+    assert cases.sha(wb.astype(np.uint8)) == str(g[f"dws_{w}_sha"])
+
+
+def test_windows_unaligned_frame_takes_gather_path(G):
+    """Frame width not a multiple of 16: no TMA descriptor possible, every window is gathered."""
+    a, b = cases.small_pair(seed=5)
+    a, b = np.ascontiguousarray(a[:285, :347]), np.ascontiguousarray(b[:285, :347])
+    rng = np.random.default_rng(1)
+    for w, o in ((32, 16), (64, 32), (16, 8)):
+        n = ((285 - w) // (w - o) + 1) * ((347 - w) // (w - o) + 1)
+        vx = rng.uniform(-9, 9, n).astype(np.float32)
+        vy = rng.uniform(-9, 9, n).astype(np.float32)
+        idx = O.window_index_grid(a.shape, w, o)
+        wa, wb = G.windows(a, b, w, o, "CWS", vx, vy)
+        assert np.array_equal(wa, O.bilinear_interpolation_cws(a, idx, -vx[:, None, None], -vy[:, None, None]))
+        assert np.array_equal(wb, O.bilinear_interpolation_cws(b, idx, vx[:, None, None], vy[:, None, None]))
+
+
+def test_reference_layout_shift_functions(T, golden):
+    """biliniar_interpolation_CWS / interpolation_DWS with the reference's own argument layout."""
+    g = golden("shift.npz")
+    for w, o in ((32, 16), (16, 8), (64, 32)):
+        fr, vx, vy = cases.shift_case(seed=w, w=w, ovl=o)
+        frame = torch.from_numpy(fr).cuda()
+        grid = T.moving_window_array(torch.arange(fr.size, dtype=torch.int64, device="cuda").reshape(fr.shape), w, o)
+        out = T.biliniar_interpolation_CWS(frame, grid, torch.from_numpy(vx)[:, None, None],
+                                           torch.from_numpy(vy)[:, None, None])
+        assert out.dtype == torch.float32 and cases.sha(out.cpu().numpy()) == str(g[f"cws_{w}_sha"])
+        ix, iy = np.rint(vx).astype(np.int64), np.rint(vy).astype(np.int64)
+        out = T.interpolation_DWS(frame, grid, torch.from_numpy(ix)[:, None, None],
+                                  torch.from_numpy(iy)[:, None, None])
+        assert out.dtype == torch.uint8 and cases.sha(out.cpu().numpy()) == str(g[f"dws_{w}_sha"])
+
+
+def test_moving_window_array(T):
+    a, _ = cases.small_pair(seed=1)
+    for w, o in cases.PASS1_GEOMS:
+        got = T.moving_window_array(torch.from_numpy(a).cuda(), w, o).cpu().numpy()
+        assert np.array_equal(got, O.moving_window_array(a, w, o))
+
+
+# ------------------------------------------------------------------------------------------
+# correlation maps
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w", [64, 32, 16])
+def test_correlate_fft(T, golden, w):
+    a, b = cases.small_pair(seed=4)
+    aa, bb = O.moving_window_array(a, w, w // 2), O.moving_window_array(b, w, w // 2)
+    ref = O.correlate_fft(aa, bb)
+    got = T.correalte_fft(torch.from_numpy(aa.copy()).cuda(), torch.from_numpy(bb.copy()).cuda())
+    assert got.dtype == torch.float32 and got.shape == ref.shape
+    assert np.abs(got.cpu().numpy() - ref).max() <= 2e-6 * np.abs(ref).max()
+    # float32 inputs (mean-normalised windows) go through the other loader
+    af = (aa / aa.mean(axis=(1, 2), keepdims=True)).astype(np.float32)
+    bf = (bb / bb.mean(axis=(1, 2), keepdims=True)).astype(np.float32)
+    ref = O.correlate_fft(af, bf)
+    got = T.correalte_fft(torch.from_numpy(af).cuda(), torch.from_numpy(bf).cuda()).cpu().numpy()
+    assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+    if w == 32:
+        head = golden("corr2disp.npz")["corr_u8_32_head"]     # reference's own correalte_fft
+        gg = T.correalte_fft(torch.from_numpy(aa[:4].copy()).cuda(), torch.from_numpy(bb[:4].copy()).cuda())
+        assert np.abs(gg.cpu().numpy() - head).max() <= 2e-6 * np.abs(head).max()
+
+
+@pytest.mark.parametrize("w,dt", [(16, np.float32), (64, np.float32), (16, np.float64), (32, np.float64)])
+def test_correlation_to_displacement_adversarial(T, golden, w, dt):
+    """Planted peaks at corners / row ends, second peaks inside and outside the 7x7 patch:
+    identical masks, float64 fit on identical inputs."""
+    g = golden("corr2disp.npz")
+    tag = f"{w}_{np.dtype(dt).name}"
+    maps = cases.adversarial_maps(seed=w + (dt == np.float64), c=400, w=w, dtype=dt)
+    dev_maps = torch.from_numpy(maps.copy()).cuda()
+    u, v, m = T.correlation_to_displacement(dev_maps, 20, 20, True)
+    assert np.array_equal(m, g[f"{tag}_mask"])
+    assert np.abs(u - g[f"{tag}_u"]).max() < 1e-9 and np.abs(v - g[f"{tag}_v"]).max() < 1e-9
+    # like the reference, the maps are modified in place (eps added, patch zeroed)
+    ref_maps = maps.copy()
+    O.correlation_to_displacement(ref_maps, 20, 20, True)
+    assert np.array_equal(dev_maps.cpu().numpy(), ref_maps)
+    u2, v2, m2 = T.correlation_to_displacement(torch.from_numpy(maps.copy()).cuda(), 20, 20, False)
+    assert m2 is None and np.array_equal(u2, u) and np.array_equal(v2, v)
+
+
+# ------------------------------------------------------------------------------------------
+# fused passes
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,zero", [("uniform", False), ("vortex", True)])
+@pytest.mark.parametrize("w,o", cases.PASS1_GEOMS)
+def test_pass_first_vs_reference(G, golden, kind, zero, w, o):
+    """extended_search_area_piv: FP32 fused kernel vs the reference's FP64 pass (golden)."""
+    g = golden("pass1.npz")
+    a, b = cases.small_pair(seed=1, kind=kind, zero_patch=zero)
+    u, v, m = G.pass_first(a, b, w, o)
+    ref = [g[f"{kind}_{w}_{o}_{k}"] for k in ("u", "v", "mask")]
+    stash = {}
+    O.extended_search_area_piv(a, b, w, o, validate=True, stash=stash)
+    check_field(u[0], v[0], m[0], *ref, stash["corr"])
+    if w >= 32:     # larger windows: every vector, invalid ones included, agrees tightly
+        assert np.array_equal(m[0], ref[2])
+        assert max(np.abs(u[0] - ref[0]).max(), np.abs(v[0] - ref[1]).max()) < 1e-4
+
+
+def test_pass_first_api(T, golden):
+    """Reference-signature wrapper: coordinates, no-validation branch, errors."""
+    g = golden("pass1.npz")
+    a, b = cases.small_pair(seed=1)
+    fa, fb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    u, v, x, y, m = T.extended_search_area_piv(fa, fb, window_size=32, overlap=16, validate=False)
+    assert m is None and u.dtype == np.float64
+    assert np.array_equal(x, g["uniform_32_16_x"]) and np.array_equal(y, g["uniform_32_16_y"])
+    assert np.abs(u - g["noval_32_16_u"]).max() < 1e-4 and np.abs(v - g["noval_32_16_v"]).max() < 1e-4
+    with pytest.raises(ValueError):
+        T.extended_search_area_piv(fa, fb, window_size=32, overlap=32)
+    with pytest.raises(ValueError):
+        T.extended_search_area_piv(fa, fb, window_size=512, overlap=0)
+    with pytest.raises(ValueError):
+        T.extended_search_area_piv(fa, fb, window_size=48, overlap=24)     # no FFT kernel: fails loudly
+
+
+@pytest.mark.parametrize("mode", ["CWS", "DWS"])
+@pytest.mark.parametrize("kind", ["uniform", "vortex"])
+def test_pass_next_function_boundary(T, golden, mode, kind):
+    """piv_iteration_{CWS,DWS}.__call__ fed with the REFERENCE's previous-pass field."""
+    g = golden(f"multipass_{mode}.npz")
+    a, b = cases.small_pair(seed=2, kind=kind)
+    fa, fb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    x, y = O.get_coordinates(a.shape, 64, 32)
+    w, o = 64, 32
+    for it in (1, 2):
+        prev = [g[f"{kind}_p{it - 1}_{k}"] for k in ("u", "v", "mask")]
+        w, o = w // 2, o // 2
+        fn = T.IterModMap.functions[mode](a.shape, w, o, "cuda:0")
+        u, v, x1, y1, m = fn(fa, fb, x, y, prev[0].copy(), prev[1].copy(), prev[2].copy())
+        assert np.array_equal(x1, g[f"{kind}_p{it}_x"]) and np.array_equal(y1, g[f"{kind}_p{it}_y"])
+        orc = O.ITER_MODES[mode](a.shape, w, o)
+        orc(a, b, x, y, prev[0].copy(), prev[1].copy(), prev[2].copy())
+        ref = [g[f"{kind}_p{it}_{k}"] for k in ("u", "v", "mask")]
+        check_field(u, v, m, *ref, orc.last_corr)
+        x, y = x1, y1
+
+
+@pytest.mark.parametrize("mode", ["CWS", "DWS"])
+def test_pass_next_without_mask(T, golden, mode):
+    g = golden(f"multipass_{mode}.npz")
+    a, b = cases.small_pair(seed=2)
+    x, y = O.get_coordinates(a.shape, 64, 32)
+    fn = T.IterModMap.functions[mode](a.shape, 32, 16, "cuda:0")
+    u, v, _, _, m = fn(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), x, y,
+                       g["uniform_p0_u"].copy(), g["uniform_p0_v"].copy(), None)
+    assert m is None
+    eu, ev = np.abs(u - g["noval_p1_u"]), np.abs(v - g["noval_p1_v"])
+    assert np.quantile(eu, 0.97) < 2e-5 and np.quantile(ev, 0.97) < 2e-5
+
+
+def test_plan_chain_vs_oracle(T):
+    """Device-resident 3-pass plan (no host round trips) vs the oracle's chained passes."""
+    for mode in ("CWS", "DWS"):
+        a, b = cases.small_pair(seed=7, kind="vortex")
+        plan = T.PIVPlan(a.shape, 64, 32, 3, mode, 2.0, device="cuda:0")
+        u, v, m = plan.run(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
+        ou, ov, _, _, om, hist = O.piv_passes(a, b, 64, 32, 3, mode)
+        for k, (hu, hv, hm) in enumerate(hist):
+            du, dv, dm = (t[0].cpu().numpy() for t in plan.pass_results(k, 1))
+            agree = (dm.astype(bool) == hm)
+            assert agree.mean() > 0.97
+            eu = np.abs(du - hu)
+            assert np.quantile(eu, 0.95) < 1e-4, (mode, k, np.quantile(eu, 0.95))
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("cws2", dict(wind_size=64, overlap=32, multipass=2, multipass_mode="CWS", dt=12, scale=0.02)),
+    ("dws2", dict(wind_size=64, overlap=32, multipass=2, multipass_mode="DWS", dt=12, scale=0.02)),
+    ("cws3", dict(wind_size=64, overlap=32, multipass=3, multipass_mode="CWS", dt=1, scale=1.0)),
+    ("single", dict(wind_size=32, overlap=16, multipass=1, dt=1, scale=1.0)),
+    ("seq_cws2", dict(wind_size=64, overlap=32, multipass=2, multipass_mode="CWS", dt=5, scale=0.5,
+                      folder_mode="sequential")),
+])
+def test_offline_piv_generator(T, golden, tmp_path, tag, kw):
+    """OfflinePIV on a bmp folder vs the reference generator's own output (golden)."""
+    from torchpiv_b200 import synth
+    g = golden("offline.npz")
+    pairs = [cases.small_pair(seed=10 + i, kind="uniform" if i % 2 == 0 else "vortex") for i in range(3)]
+    synth.write_pair_folder(str(tmp_path), pairs)
+    gen = T.OfflinePIV(folder=str(tmp_path), device="cuda:0", file_fmt="bmp", **kw)
+    res = list(gen())
+    assert (len(gen), len(res)) == tuple(g[f"{tag}_n"])
+    k = kw["scale"] / kw["dt"] * 1000
+    for i, (x, y, u, v) in enumerate(res):
+        assert u.dtype == np.float64 and u.shape == g[f"{tag}_{i}_u"].shape
+        assert np.array_equal(x, g[f"{tag}_{i}_x"]) and np.array_equal(y, g[f"{tag}_{i}_y"])
+        du = np.abs(u - g[f"{tag}_{i}_u"]) / k
+        dv = np.abs(v - g[f"{tag}_{i}_v"]) / k
+        # chained passes + Qhull hole filling: the bulk is tight, vectors next to replaced ones looser
+        assert np.quantile(du, 0.95) < 1e-4 and np.quantile(dv, 0.95) < 1e-4
+        assert np.quantile(du, 0.995) < 5e-2 and np.quantile(dv, 0.995) < 5e-2
+
+
+# ------------------------------------------------------------------------------------------
+# full-size (BASELINE.json) properties that need no oracle
+# ------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def big_pair():
+    from torchpiv_b200 import synth
+    shape = (2048, 2048)
+    noise, blank = synth.default_patches(shape)
+    return synth.particle_pair(shape, synth.uniform_shift(3.3, -2.2), seed=0, noise_patch=noise,
+                               blank_patch=blank)
+
+
+@pytest.mark.parametrize("mode,passes", [("CWS", 1), ("CWS", 2), ("DWS", 2), ("CWS", 3)])
+def test_full_size_known_displacement(T, big_pair, mode, passes):
+    """4 MP synthetic pair with an imposed uniform shift (+3.3, -2.2) px: recovered within the
+    reference's own accuracy (~0.05 px)."""
+    a, b = big_pair
+    plan = T.PIVPlan(a.shape, 64, 32, passes, mode, 2.0, device="cuda:0")
+    u, v, m = (t[0].cpu().numpy() for t in plan.run(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()))
+    ok = ~m.astype(bool)
+    g = plan.out_geometry
+    assert u.shape == (g.n_rows, g.n_cols) == {1: (63, 63), 2: (127, 127), 3: (255, 255)}[passes]
+    assert 0.002 < 1 - ok.mean() < 0.12          # noise + blank patches are flagged, the rest is not
+    assert abs(np.median(u[ok]) - 3.3) < 0.1 and abs(np.median(v[ok]) + 2.2) < 0.1
+    assert np.sqrt(np.mean((u[ok] - 3.3) ** 2)) < 0.35
+
+
+def test_full_size_batch_invariance_and_determinism(T, big_pair):
+    """Results do not depend on batch size, batch position, or run: pairs are independent."""
+    a, b = big_pair
+    fa, fb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    plan = T.PIVPlan(a.shape, 64, 32, 2, "CWS", 2.0, device="cuda:0")
+    u1, v1, m1 = (t.clone() for t in plan.run(fa, fb))
+    fa4 = torch.stack([fa, fb, fa, fa.flip(0)])
+    fb4 = torch.stack([fb, fa, fb, fb.flip(0)])
+    u4, v4, m4 = (t.clone() for t in plan.run(fa4, fb4))
+    for i in (0, 2):
+        assert torch.equal(u4[i], u1[0]) and torch.equal(v4[i], v1[0]) and torch.equal(m4[i], m1[0])
+    u4b, v4b, m4b = plan.run(fa4, fb4)
+    assert torch.equal(u4b, u4) and torch.equal(v4b, v4) and torch.equal(m4b, m4)
+    # swapping the frames flips the sign of the first-pass field (circular correlation symmetry)
+    p1 = T.PIVPlan(a.shape, 64, 32, 1, "CWS", 2.0, device="cuda:0")
+    ua, va, ma = (t.clone() for t in p1.run(fa, fb))
+    ub, vb, mb = p1.run(fb, fa)
+    ok = (~ma.bool()) & (~mb.bool())
+    assert ok.float().mean() > 0.9
+    assert (ua + ub)[ok].abs().median() < 0.05 and (va + vb)[ok].abs().median() < 0.05
+
+
+def test_full_size_against_oracle(T, big_pair):
+    """One 4 MP 2-pass CWS pair end to end vs the oracle (about 3 s of CPU)."""
+    a, b = big_pair
+    plan = T.PIVPlan(a.shape, 64, 32, 2, "CWS", 2.0, device="cuda:0")
+    u, v, m = (t[0].cpu().numpy() for t in plan.run(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()))
+    ou, ov, _, _, om, _ = O.piv_passes(a, b, 64, 32, 2, "CWS")
+    assert (m.astype(bool) != om).mean() < 2e-3
+    ok = ~om & ~m.astype(bool)
+    eu, ev = np.abs(u - ou)[ok], np.abs(v - ov)[ok]
+    assert np.quantile(eu, 0.999) < 1e-4 and np.quantile(ev, 0.999) < 1e-4
+    assert eu.max() < 5e-2 and ev.max() < 5e-2
+
+
+# ------------------------------------------------------------------------------------------
+# edge cases
+# ------------------------------------------------------------------------------------------
+def test_degenerate_frames(G):
+    """Black, constant and saturated frames: the reference's NaN / all-ties behaviour."""
+    shape = (96, 128)
+    z = np.zeros(shape, np.uint8)
+    c = np.full(shape, 10, np.uint8)
+    s = np.full(shape, 255, np.uint8)
+    for a, b in ((z, z), (c, c), (s, c), (z, c)):
+        u, v, m = G.pass_first(a, b, 32, 16)
+        ru, rv, _, _, rm = O.extended_search_area_piv(a, b, 32, 16, validate=True)
+        assert np.array_equal(u[0], ru) and np.array_equal(v[0], rv) and np.array_equal(m[0], rm)
+
+
+def test_single_window_and_small_fields(G, T):
+    a, b = cases.small_pair(seed=1)
+    a, b = np.ascontiguousarray(a[:64, :64]), np.ascontiguousarray(b[:64, :64])
+    u, v, m = G.pass_first(a, b, 64, 32)
+    ru, rv, _, _, rm = O.extended_search_area_piv(a, b, 64, 32, validate=True)
+    assert u.shape == (1, 1, 1) and abs(u[0, 0, 0] - ru[0, 0]) < 1e-4 and m[0, 0, 0] == rm[0, 0]
+    with pytest.raises(ValueError):      # bicubic predictor needs >= 4 points per axis (FITPACK too)
+        T.PIVPlan((64, 64), 64, 32, 2, "CWS", 2.0, device="cuda:0")
+
+
+def test_huge_and_nonfinite_predictor_is_clamped(T):
+    """Absurd predictor values (|shift| > 2^20 px) are clamped instead of overflowing."""
+    a, b = cases.small_pair(seed=2)
+    x, y = O.get_coordinates(a.shape, 64, 32)
+    u0 = np.full(x.shape, 3.0e9)
+    v0 = np.full(x.shape, -3.0e9)
+    fn = T.piv_iteration_CWS(a.shape, 32, 16, "cuda:0")
+    u, v, _, _, m = fn(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), x, y, u0, v0,
+                       np.zeros(x.shape, bool))
+    assert np.isfinite(u).all() and np.isfinite(v).all() and m.all()   # featureless windows: invalid
+
+
+def test_error_codes_through_c_abi(G):
+    from torchpiv_b200 import _lib
+    L = _lib.lib()
+    t = torch.zeros((64, 64), dtype=torch.uint8, device="cuda")
+    o = torch.zeros(16, dtype=torch.float64, device="cuda")
+    mk = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    args = lambda w, ov: (t.data_ptr(), t.data_ptr(), 1, 0, 64, 64, 64, w, ov, 1, 1.2, o.data_ptr(),  # noqa: E731
+                          o.data_ptr(), mk.data_ptr(), None, None)
+    assert L.pivb200_pass_first(*args(48, 24)) == _lib.E_WINDOW
+    assert L.pivb200_pass_first(*args(32, 32)) == _lib.E_OVERLAP
+    assert L.pivb200_pass_first(*args(128, 0)) == _lib.E_WINDOW
+    assert L.pivb200_pass_first(*args(64, 0)) == 0
+    bad = list(args(32, 16)); bad[11] = None
+    assert L.pivb200_pass_first(*bad) == _lib.E_ARG
+    torch.cuda.synchronize()
+
+
+def test_native_library_is_what_ran():
+    """The tests above went through libpivb200.so: it is loaded and counted launches."""
+    from torchpiv_b200 import _lib
+    assert _lib.launch_count() > 0
+    with open("/proc/self/maps") as fh:
+        assert any("libpivb200.so" in line for line in fh)
+    assert os.path.isfile(_lib.LIB_PATH)

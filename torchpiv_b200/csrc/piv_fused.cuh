@@ -398,6 +398,12 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
         const int col1 = kc, col2 = kc ? W - kc : HALF;
         float2* const Mw = reinterpret_cast<float2*>(smem + S::EX_OFF + wi * G::MB);
         float sum_a = 0.f, sum_b = 0.f;        // pixel sums of the window (valid in lanes kc == 0)
+        // bit w set: window w of the job is exactly constant in frame a (b).  The reference then gets
+        // an exactly constant correlation map (all ties -> peak index 0, ratio 1); packing a + i b
+        // into one transform would leak ~1e-7 of the other frame into it, so such windows are
+        // detected here and their map is forced to zero.
+        unsigned const_a = 0xffffffffu, const_b = 0xffffffffu;
+        float lead_a = 0.f, lead_b = 0.f;
         float2 x[W];                           // the FFT operand
         float2 xs[(W <= 32) ? W : 1];          // W <= 32: spectrum of column k kept while column W-k is transformed
         constexpr int NSTEP = (SINK == SK_WIN) ? 2 : 6;
@@ -520,6 +526,31 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                 __syncwarp();                   // Q fully read before the map overwrites it
             }
 
+            if (s < 2 && SINK == SK_DISP) {
+                uint32_t da = 0u, db = 0u;
+                static_for<1, W>([&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    da |= __float_as_uint(x[j].x) ^ __float_as_uint(x[0].x);
+                    db |= __float_as_uint(x[j].y) ^ __float_as_uint(x[0].y);
+                });
+                constexpr int SEG = (W < 32) ? W : 32;             // lanes holding rows of one window
+                const int seg_lane0 = lane & ~(SEG - 1);
+                // first pixel of the window: row 0 is read in step 0 for W = 64, in this step otherwise
+                if (W < 64 || s == 0) {
+                    lead_a = __shfl_sync(FULL, x[0].x, seg_lane0);
+                    lead_b = __shfl_sync(FULL, x[0].y, seg_lane0);
+                }
+                const unsigned oka = __ballot_sync(FULL, da == 0u && x[0].x == lead_a);
+                const unsigned okb = __ballot_sync(FULL, db == 0u && x[0].y == lead_b);
+#pragma unroll
+                for (int k = 0; k < 32 / SEG; ++k) {
+                    const unsigned segmask = (SEG == 32) ? 0xffffffffu : (((1u << SEG) - 1u) << (k * SEG));
+                    const int wdx = ((32 * s + k * SEG) >> LOGW) & (NW - 1);
+                    if ((oka & segmask) != segmask) const_a &= ~(1u << wdx);
+                    if ((okb & segmask) != segmask) const_b &= ~(1u << wdx);
+                }
+            }
+
             if constexpr (SINK == SK_WIN) {
                 if (active && job_c * NW + rwi < n_total) {
                     float4* oa = reinterpret_cast<float4*>(p.win_a_out + (static_cast<long long>(g) * W + rt) * W);
@@ -529,6 +560,10 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                         oa[c] = make_float4(x[4 * c].x, x[4 * c + 1].x, x[4 * c + 2].x, x[4 * c + 3].x);
                         ob[c] = make_float4(x[4 * c].y, x[4 * c + 1].y, x[4 * c + 2].y, x[4 * c + 3].y);
                     });
+                }
+                if (s == 1) {
+                    __syncwarp();
+                    if (base + job_stride < njobs) stage_tiles(min(job + job_stride, njobs - 1), buf ^ 1);
                 }
                 continue;
             }
@@ -603,10 +638,12 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
         // raw row l -> shifted row l + W/2 (values x[].y); raw row l + W/2 -> shifted row l (x[].x)
         float* mapw = reinterpret_cast<float*>(smem + S::EX_OFF + wi * G::MB);
         float mx_hi = -FLT_MAX, mx_lo = -FLT_MAX, mn = FLT_MAX;     // hi: shifted row l + HALF
+        const bool degenerate = ((const_a | const_b) >> wi) & 1u;
         static_for<0, W>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
             constexpr int sc = (j + HALF) % W;
-            const float2 o = x[F::pos(j)];
+            float2 o = x[F::pos(j)];
+            if (SINK == SK_DISP && degenerate) o = make_float2(0.f, 0.f);
             mapw[(l + HALF) * PC + sc] = o.y;
             mapw[l * PC + sc] = o.x;
             mx_hi = fmaxf(mx_hi, o.y);
