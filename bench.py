@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""Benchmark of the PIV cross-correlation hot path (BASELINE.json metric:
+4 MP pairs/s, 64 px windows, 50 % overlap, 2-pass CWS).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the hot path (pass 1 at 64/32 + predictor + CWS pass 2 at 32/16) over
+one batch of PAIRS_PER_STEP synthetic 2048x2048 particle-image pairs per GPU.
+
+  value : whole-job pairs/s with the frames already resident in HBM (CUDA events on the launch
+          stream, barrier + synchronize on both sides, max over ranks).  The batch (2 x 32 x 4 MB
+          = 268 MB of frames) is larger than the 126 MB L2, so every step re-reads it from HBM.
+  e2e   : the same metric through the public host API (HostPipeline: pinned host frames -> H2D ->
+          fused kernels -> D2H of u, v, mask), copies inside the timed region every step.
+  roofline     : dominant kernel (CWS pass at 32 px) against the FFMA peak measured in this run.
+  cpu_baseline : the CPU oracle (NumPy/SciPy port of the reference path, all host threads) on a
+                 bounded sample of the same workload, rank 0 only.
+
+Multi-GPU (torchrun, one rank per GPU): pairs are independent, so each rank processes its own
+shard of pairs (weak scaling); torch.distributed is used for the barrier and the max-over-ranks
+of the device time only -- there is no collective on the data path.
+
+--impl reference times the reference's own algorithm on the host cores (the CPU oracle; the
+reference is pure Python/PyTorch and cannot travel to the GPU box -- see DESIGN.md).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SHAPE = (2048, 2048)
+WIND, OVERLAP, PASSES, MODE, SCALE = 64, 32, 2, "CWS", 2.0
+PAIRS_PER_STEP = 32          # per GPU; 268 MB of frames > L2
+UNIQUE_PAIRS = 4             # rendered on the host, then rolled into PAIRS_PER_STEP distinct pairs
+METRIC = "4MP pairs/sec (64px, 50% ovl, 2-pass CWS)"
+WORKLOAD = ("synthetic 2048x2048 uniform-shift particle pairs (+3.3,-2.2 px, noise + blank patch), "
+            "64->32 px windows, 50% overlap, 2-pass CWS")
+
+
+def flops_per_window(w: int) -> float:
+    """three real 2-D transforms + half-spectrum conjugate multiply."""
+    return 15.0 * w * w * np.log2(w) + 6.0 * w * (w / 2 + 1)
+
+
+def pass_geometry():
+    from torchpiv_b200.engine import pass_schedule
+    out = []
+    for w, o in pass_schedule(WIND, OVERLAP, PASSES, SCALE):
+        n = ((SHAPE[0] - w) // (w - o) + 1) * ((SHAPE[1] - w) // (w - o) + 1)
+        out.append((w, o, n))
+    return out
+
+
+def make_pairs(n_unique: int, seed0: int = 0):
+    from torchpiv_b200 import synth
+    noise, blank = synth.default_patches(SHAPE)
+    return [synth.particle_pair(SHAPE, synth.uniform_shift(3.3, -2.2), seed=seed0 + i,
+                                noise_patch=noise, blank_patch=blank) for i in range(n_unique)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(n_pairs: int, warmup: int = 0):
+    """pairs/s of the CPU oracle (2-pass CWS, all host threads) on n_pairs 4 MP pairs."""
+    from oracle import piv_oracle as O
+    pairs = make_pairs(min(n_pairs, 2), seed0=100)
+    iters = [O.ITER_MODES[MODE](SHAPE, w, o, workers=-1) for (w, o, _) in pass_geometry()[1:]]
+    for i in range(warmup):
+        a, b = pairs[i % len(pairs)]
+        O.piv_passes(a, b, WIND, OVERLAP, PASSES, MODE, SCALE, workers=-1, iter_objs=iters)
+    t0 = time.perf_counter()
+    for i in range(n_pairs):
+        a, b = pairs[i % len(pairs)]
+        O.piv_passes(a, b, WIND, OVERLAP, PASSES, MODE, SCALE, workers=-1, iter_objs=iters)
+    dt = time.perf_counter() - t0
+    return n_pairs / dt, dt
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pairs_per_step = 1
+    rate, dt = cpu_oracle_rate(args.steps * pairs_per_step, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "pairs_per_step": pairs_per_step, "device": "cpu",
+                   "note": "reference algorithm on the host cores (CPU oracle port, scipy.fft, all threads)"},
+        "cpu_baseline": {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} x 1 4MP pair, 2-pass CWS, pass functions only (no image decode)"},
+        "e2e": {"value": rate, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import torchpiv_b200 as T
+    from torchpiv_b200 import _lib
+    from torchpiv_b200.engine import HostPipeline
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: torchpiv_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    B = args.pairs_per_step
+    # ---- synthetic data: a few rendered pairs, rolled into B distinct pairs per rank -----------
+    base = make_pairs(UNIQUE_PAIRS, seed0=1000 * rank)
+    host_a = torch.empty((B,) + SHAPE, dtype=torch.uint8).pin_memory()
+    host_b = torch.empty((B,) + SHAPE, dtype=torch.uint8).pin_memory()
+    for i in range(B):
+        a, b = base[i % UNIQUE_PAIRS]
+        sh = (37 * (i // UNIQUE_PAIRS), 53 * (i // UNIQUE_PAIRS))
+        host_a[i].copy_(torch.from_numpy(np.roll(a, sh, axis=(0, 1))))
+        host_b[i].copy_(torch.from_numpy(np.roll(b, sh, axis=(0, 1))))
+    fa, fb = host_a.to(dev), host_b.to(dev)
+
+    plan = T.PIVPlan(SHAPE, WIND, OVERLAP, PASSES, MODE, SCALE, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    # ---- device-resident timing -----------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        plan.run(fa, fb)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        plan.run(fa, fb)
+    e1.record(stream)
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # sanity: the benchmarked computation produced the imposed displacement
+    u, v, m = plan.run(fa[:1], fb[:1])
+    ok = ~m[0].bool()
+    med_u, med_v = float(u[0][ok].median()), float(v[0][ok].median())
+    if abs(med_u - 3.3) > 0.1 or abs(med_v + 2.2) > 0.1:
+        raise SystemExit(f"benchmark output is wrong: median displacement {med_u:.3f}, {med_v:.3f}")
+
+    # ---- end to end through the host API --------------------------------------------------------
+    pipe = HostPipeline(plan, B)
+    for _ in range(2):
+        pipe.result(pipe.submit(host_a, host_b))
+    barrier()
+    h0, d0 = pipe.h2d_bytes, pipe.d2h_bytes
+    t0 = time.perf_counter()
+    pending = None
+    checksum = 0.0
+    for _ in range(args.steps):
+        sid = pipe.submit(host_a, host_b)
+        if pending is not None:
+            ru, rv, rm = pipe.result(pending)
+            checksum += float(ru[0, 0, 0])
+        pending = sid
+    ru, rv, rm = pipe.result(pending)
+    checksum += float(ru[0, 0, 0])
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_ms = max_over_ranks(e2e_s * 1e3)
+    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+    h2d_step = (pipe.h2d_bytes - h0) // args.steps
+    d2h_step = (pipe.d2h_bytes - d0) // args.steps
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (rank 0, timed alone on its stream) --------------------
+    import ctypes
+    geo = pass_geometry()
+    ws = plan._ws
+
+    def time_kernel(fn, reps=5):
+        fn()
+        torch.cuda.synchronize(dev)
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record(stream)
+        for _ in range(reps):
+            fn()
+        k1.record(stream)
+        torch.cuda.synchronize(dev)
+        return k0.elapsed_time(k1) / reps
+
+    L = _lib.lib()
+    st = stream.cuda_stream
+    w0, w1 = ws[0], ws[1]
+    g0, g1 = plan.passes[0], plan.passes[1]
+    ps, pitch = fa.stride(0), fa.stride(1)
+
+    def k_first():
+        _lib.check(L.pivb200_pass_first(fa.data_ptr(), fb.data_ptr(), B, ps, SHAPE[0], SHAPE[1], pitch, g0.wind,
+                                        g0.overlap, 1, 1.2, w0["u"].data_ptr(), w0["v"].data_ptr(),
+                                        w0["mask"].data_ptr(), None, st))
+
+    def k_next():
+        _lib.check(L.pivb200_pass_next(fa.data_ptr(), fb.data_ptr(), B, ps, SHAPE[0], SHAPE[1], pitch, g1.wind,
+                                       g1.overlap, plan.mode, w1["sx"].data_ptr(), w1["sy"].data_ptr(),
+                                       w1["base_u"].data_ptr(), w1["base_v"].data_ptr(), w1["pred_u"].data_ptr(),
+                                       w1["pred_v"].data_ptr(), 1, 1.2, w1["u"].data_ptr(), w1["v"].data_ptr(),
+                                       w1["mask"].data_ptr(), None, st))
+
+    ms_first, ms_next = time_kernel(k_first), time_kernel(k_next)
+    peak = ctypes.c_double()
+    _lib.check(L.pivb200_measure_fp32_peak(10, ctypes.byref(peak), st))
+    flops_first = B * geo[0][2] * flops_per_window(geo[0][0])
+    flops_next = B * geo[1][2] * flops_per_window(geo[1][0])
+    achieved = flops_next / (ms_next * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("pass_next_cws_w32_dram_bytes_per_pair")
+            traffic = traffic * B if traffic is not None else None
+        except (OSError, ValueError):
+            traffic = None
+    peaks = {}
+    ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(ppath):
+        peaks = json.load(open(ppath))
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    bytes_next = B * (2 * SHAPE[0] * SHAPE[1] + 18 * geo[1][2])
+    roofline = {"bound": "fp32", "kernel": "piv_fused_kernel<32, CWS, DISP> (pass 2)", "achieved": achieved,
+                "peak": peak.value, "peak_source": "FFMA micro-benchmark run by this bench.py (MEASURED_PEAKS.json has no FP32 figure)",
+                "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": traffic,
+                "ms_per_launch": ms_next, "algorithmic_flops_per_launch": flops_next,
+                "share_of_step": ms_next / (ms_total / args.steps),
+                "pass_first": {"ms_per_launch": ms_first, "achieved": flops_first / (ms_first * 1e-3) / 1e12,
+                               "frac": flops_first / (ms_first * 1e-3) / 1e12 / peak.value},
+                "whole_step_frac": (flops_first + flops_next) / (ms_total / args.steps * 1e-3) / 1e12 / peak.value,
+                "hbm": {"achieved": bytes_next / (ms_next * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": bytes_next / (ms_next * 1e-3) / 1e9 / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}}
+
+    # ---- CPU baseline (bounded sample) ----------------------------------------------------------
+    cores = os.cpu_count() or 1
+    n_cpu = args.cpu_pairs
+    cpu_rate, cpu_dt = cpu_oracle_rate(n_cpu, warmup=1)
+    line = {
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": B, "frame_bytes_per_step_per_gpu": 2 * B * SHAPE[0] * SHAPE[1],
+                   "l2_policy": "inputs larger than L2 (268 MB of frames per step vs 126 MB L2)",
+                   "sharding": "pairs split across ranks, no data-path collective"},
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_step),
+                "d2h_bytes_per_step": int(d2h_step), "ms_per_step": e2e_ms / args.steps,
+                "api": "torchpiv_b200.engine.HostPipeline (pinned host frames in, u/v/mask on the host out)"},
+        "gpu_launches": int(launches), "launches_per_step": plan.launches_per_batch,
+        "clocks": clocks, "roofline": roofline,
+        "cpu_baseline": {"value": cpu_rate, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_cpu} 4MP pairs, 2-pass CWS pass functions (CPU oracle, scipy.fft workers=-1), {cpu_dt:.1f} s"},
+        "check": {"median_u_px": med_u, "median_v_px": med_v, "imposed": [3.3, -2.2]},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs-per-step", type=int, default=PAIRS_PER_STEP)
+    ap.add_argument("--cpu-pairs", type=int, default=4, help="size of the bounded CPU-baseline sample")
+    args = ap.parse_args()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

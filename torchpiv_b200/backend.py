@@ -321,6 +321,7 @@ class OfflinePIV:
         self._iter_function = IterModMap.functions[multipass_mode]   # KeyError for unknown modes
         self._mode = multipass_mode
         self._plan = None
+        self._pipe = None
         if not len(self):
             return
         self._device = _cuda_device(self._device)
@@ -336,22 +337,36 @@ class OfflinePIV:
         return len(self._dataset)
 
     def __call__(self) -> Generator:
-        dev = self._device
-        for index in range(len(self._dataset)):
-            a, b = self._dataset[index]
-            if a is None or b is None:
-                continue
-            if self._plan is None or (self._plan.H, self._plan.W) != a.shape:
-                self._plan = self._make_plan(a.shape)
-            plan = self._plan
-            fa = torch.from_numpy(a).to(dev, non_blocking=True)
-            fb = torch.from_numpy(b).to(dev, non_blocking=True)
-            u_d, v_d, m_d = plan.run(fa, fb)
-            u = u_d[0].cpu().numpy()
-            v = v_d[0].cpu().numpy()
-            val = m_d[0].cpu().numpy().astype(bool)
-            geo = plan.out_geometry
-            out = finalize_field(u, v, geo.x, geo.y, val, self._scale, self._dt)
-            if out is None:
-                continue
-            yield out
+        """Yield ``(x, y, u, v)`` per processed pair, in pair order.  Image decoding runs two pairs
+        ahead on a helper thread (OpenCV releases the GIL) while the GPU works on the current one."""
+        from concurrent.futures import ThreadPoolExecutor
+        n = len(self._dataset)
+        if n == 0:
+            return
+        with ThreadPoolExecutor(max_workers=2) as pool:
+            ahead = [pool.submit(self._dataset.__getitem__, i) for i in range(min(2, n))]
+            for index in range(n):
+                a, b = ahead.pop(0).result()
+                if index + 2 < n:
+                    ahead.append(pool.submit(self._dataset.__getitem__, index + 2))
+                if a is None or b is None:
+                    continue
+                out = self._process(a, b)
+                if out is None:
+                    continue
+                yield out
+
+    def _process(self, a: np.ndarray, b: np.ndarray):
+        """One decoded pair -> (x, y, u, v) or None (pair skipped, see postprocess.fill_holes)."""
+        if self._plan is None or (self._plan.H, self._plan.W) != a.shape:
+            self._plan = self._make_plan(a.shape)
+            self._pipe = None
+        if getattr(self, "_pipe", None) is None:
+            from .engine import HostPipeline
+            self._pipe = HostPipeline(self._plan, 1)
+            self._pin = [torch.empty((1,) + tuple(a.shape), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self._pin[0][0].copy_(torch.from_numpy(a))
+        self._pin[1][0].copy_(torch.from_numpy(b))
+        u, v, val = self._pipe.result(self._pipe.submit(self._pin[0], self._pin[1]))
+        geo = self._plan.out_geometry
+        return finalize_field(u[0].copy(), v[0].copy(), geo.x, geo.y, val[0], self._scale, self._dt)

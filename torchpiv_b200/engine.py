@@ -180,3 +180,68 @@ class PIVPlan:
                 raise ValueError("frame rows must be contiguous")
         if a.shape != b.shape or a.stride() != b.stride():
             raise ValueError("frame_a and frame_b batches must have identical shape and strides")
+
+
+class HostPipeline:
+    """End-to-end batches from HOST memory: pinned staging -> H2D -> PIVPlan -> D2H of the result.
+
+    Two slots are cycled so that the copy-in of batch i+1 (copy stream) overlaps the kernels of
+    batch i (compute stream); every batch still pays its own H2D and D2H.  This is the path
+    ``OfflinePIV`` and ``bench.py``'s ``e2e`` number go through."""
+
+    def __init__(self, plan: PIVPlan, max_pairs: int):
+        self.plan = plan
+        dev = plan.device
+        g = plan.out_geometry
+        self.max_pairs = int(max_pairs)
+        self.compute = torch.cuda.Stream(dev)
+        self.copy = torch.cuda.Stream(dev)
+        self.slots = []
+        for _ in range(2):
+            self.slots.append({
+                "a": torch.empty((max_pairs, plan.H, plan.W), dtype=torch.uint8, device=dev),
+                "b": torch.empty((max_pairs, plan.H, plan.W), dtype=torch.uint8, device=dev),
+                "u": torch.empty((max_pairs, g.n_rows, g.n_cols), dtype=torch.float64).pin_memory(),
+                "v": torch.empty((max_pairs, g.n_rows, g.n_cols), dtype=torch.float64).pin_memory(),
+                "m": torch.empty((max_pairs, g.n_rows, g.n_cols), dtype=torch.uint8).pin_memory(),
+                "in_ready": torch.cuda.Event(), "done": torch.cuda.Event(), "free": torch.cuda.Event(),
+                "n": 0,
+            })
+        self._next = 0
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def submit(self, host_a: torch.Tensor, host_b: torch.Tensor) -> int:
+        """Enqueue one batch (pinned uint8 ``[B, H, W]`` host tensors).  Returns the slot id to
+        pass to :meth:`result`.  At most two batches may be in flight."""
+        B = host_a.shape[0]
+        if B > self.max_pairs:
+            raise ValueError("batch larger than the pipeline was built for")
+        sid = self._next
+        self._next ^= 1
+        s = self.slots[sid]
+        with torch.cuda.stream(self.copy):
+            self.copy.wait_event(s["free"])            # previous user of this slot has been read back
+            s["a"][:B].copy_(host_a, non_blocking=True)
+            s["b"][:B].copy_(host_b, non_blocking=True)
+            s["in_ready"].record(self.copy)
+        with torch.cuda.stream(self.compute):
+            self.compute.wait_event(s["in_ready"])
+            u, v, m = self.plan.run(s["a"][:B], s["b"][:B], stream=self.compute.cuda_stream)
+            s["u"][:B].copy_(u, non_blocking=True)
+            s["v"][:B].copy_(v, non_blocking=True)
+            s["m"][:B].copy_(m, non_blocking=True)
+            s["done"].record(self.compute)
+            s["free"].record(self.compute)
+        s["n"] = B
+        self.h2d_bytes += 2 * host_a[:B].numel()
+        self.d2h_bytes += B * (s["u"][0].numel() * 16 + s["m"][0].numel())
+        return sid
+
+    def result(self, sid: int):
+        """Block until batch ``sid`` is back on the host; returns NumPy views ``(u, v, invalid)``
+        (valid until the slot is reused two submits later)."""
+        s = self.slots[sid]
+        s["done"].synchronize()
+        B = s["n"]
+        return s["u"][:B].numpy(), s["v"][:B].numpy(), s["m"][:B].numpy().astype(bool)
