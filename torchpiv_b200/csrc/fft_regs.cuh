@@ -133,18 +133,29 @@ __host__ __device__ constexpr int pick_radix() {
 }
 
 // ----------------------------------------------------------------------------------------
-// Dif<N, S, O, T>: forward FFT of the N elements x[O + j*S] of a T-element register array.
-// Bin k ends up at x[O + S * pos(k)].
+// Register views: the transform addresses logical element i at physical slot V::at(i).  Since every
+// index is a compile-time constant a permuted view costs nothing, which is what lets a transform
+// consume data that a previous transform left in digit-reversed order (no reordering pass).
 // ----------------------------------------------------------------------------------------
-template <int N, int S, int O, int T>
+struct ViewId {
+    __host__ __device__ static constexpr int at(int i) { return i; }
+};
+
+// ----------------------------------------------------------------------------------------
+// Dif<N, S, O, T, V>: forward FFT of the N logical elements O + j*S of a T-element register array.
+// Bin k ends up at logical position O + S * pos(k), i.e. physical slot V::at(O + S * pos(k)).
+// ----------------------------------------------------------------------------------------
+template <int N, int S, int O, int T, class V = ViewId>
 struct Dif {
     static constexpr int R = pick_radix<N>();
     static constexpr int M = N / R;
 
     __host__ __device__ static constexpr int pos(int k) {
         if constexpr (M == 1) return k;
-        else return M * (k % R) + Dif<M, S, O, T>::pos(k / R);
+        else return M * (k % R) + Dif<M, S, O, T, V>::pos(k / R);
     }
+    // physical slot of bin k of a whole-array transform (S = 1, O = 0)
+    __host__ __device__ static constexpr int slot(int k) { return V::at(pos(k)); }
 
     __host__ __device__ static __forceinline__ void run(float2 (&x)[T]) {
         static_for<0, M>([&](auto jc) {
@@ -152,19 +163,19 @@ struct Dif {
             float2 a[R];
             static_for<0, R>([&](auto qc) {
                 constexpr int q = decltype(qc)::value;
-                a[q] = x[O + (j + M * q) * S];
+                a[q] = x[V::at(O + (j + M * q) * S)];
             });
             dft_small<R>(a);
             static_for<0, R>([&](auto pc) {
                 constexpr int p = decltype(pc)::value;
-                if constexpr (M > 1) x[O + (j + M * p) * S] = mul_tw<j * p, N>(a[p]);
-                else x[O + (j + M * p) * S] = a[p];
+                if constexpr (M > 1) x[V::at(O + (j + M * p) * S)] = mul_tw<j * p, N>(a[p]);
+                else x[V::at(O + (j + M * p) * S)] = a[p];
             });
         });
         if constexpr (M > 1) {
             static_for<0, R>([&](auto pc) {
                 constexpr int p = decltype(pc)::value;
-                Dif<M, S, O + M * p * S, T>::run(x);
+                Dif<M, S, O + M * p * S, T, V>::run(x);
             });
         }
     }
@@ -172,5 +183,14 @@ struct Dif {
 
 template <int N>
 using Fft = Dif<N, 1, 0, N>;
+
+// View that reads logical element j from the slot where Fft<N> left bin j: FftRev<N> transforms
+// the OUTPUT of an Fft<N> in place (bin k of the second transform lands at FftRev<N>::slot(k)).
+template <int N>
+struct ViewRev {
+    __host__ __device__ static constexpr int at(int i) { return Fft<N>::pos(i); }
+};
+template <int N>
+using FftRev = Dif<N, 1, 0, N, ViewRev<N>>;
 
 }  // namespace pivb200

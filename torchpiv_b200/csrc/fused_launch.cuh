@@ -29,12 +29,7 @@ namespace pivb200 {
 template <int W, int LOADER, int SINK>
 static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const PassParams& p_in,
                       cudaStream_t stream) {
-    PassParams p = p_in;
-    {
-        // lock-step barriers (see piv_fused.cuh); PIVB200_SYNC_MASK overrides for experiments
-        static const int env_mask = [] { const char* e = getenv("PIVB200_SYNC_MASK"); return e ? atoi(e) : -1; }();
-        p.sync_mask = env_mask >= 0 ? env_mask : (1 << 2);      // measured best on B200: one barrier per job
-    }
+    const PassParams& p = p_in;
     using S = Smem<W, LOADER>;
     auto kern = piv_fused_kernel<W, LOADER, SINK>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::CTA_BYTES);
@@ -44,9 +39,12 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const PassPa
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     // persistent: one CTA of NWARPS warps per SM, each warp strides over the jobs
     const long long njobs = (p.n_total + Geo<W>::NW - 1) / Geo<W>::NW;
-    long long grid = (njobs + S::NWARPS - 1) / S::NWARPS;
+    // PIVB200_NWARPS caps the warps per CTA (occupancy experiments)
+    static const int env_warps = [] { const char* e = getenv("PIVB200_NWARPS"); return e ? atoi(e) : 0; }();
+    const int nwarps = (env_warps > 0 && env_warps < S::NWARPS) ? env_warps : S::NWARPS;
+    long long grid = (njobs + nwarps - 1) / nwarps;
     if (grid > sms) grid = sms;
-    kern<<<static_cast<unsigned>(grid), S::NWARPS * 32, S::CTA_BYTES, stream>>>(ta, tb, p);
+    kern<<<static_cast<unsigned>(grid), nwarps * 32, S::CTA_BYTES, stream>>>(ta, tb, p);
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }

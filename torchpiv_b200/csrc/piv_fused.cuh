@@ -1,7 +1,7 @@
-// Fused PIV pass kernel for sm_100a: window extraction (TMA 2-D/3-D tile loads of the uint8
-// frame) -> CWS bilinear / DWS integer window shift -> 2-D cross-correlation by in-register
-// FFTs -> fft-shifted peak search, 3-point log-Gaussian sub-pixel fit, peak-ratio validation
-// and predictor glue.  Only the displacement vectors leave the SM.
+// Fused PIV pass kernel for sm_100a: window extraction (TMA 3-D tile loads of the uint8 frames)
+// -> CWS bilinear / DWS integer window shift -> 2-D cross-correlation by in-register FFTs ->
+// fft-shifted peak search, 3-point log-Gaussian sub-pixel fit, peak-ratio validation and predictor
+// glue.  Only the displacement vectors leave the SM.
 //
 // Replaces, for one pass, the reference's eager op chain
 //   moving_window_array (PB:220-247) -> [biliniar_interpolation_CWS | interpolation_DWS]
@@ -9,15 +9,23 @@
 //   correlation_to_displacement + peak2peak_secondpeak (PB:346-422) -> replacement logic
 //   (PB:728-738 / 800-810).
 //
-// Execution model: one WARP owns a "job" of NW = 64 / W interrogation windows (W = 64/32/16)
-// and is persistent over jobs; a CTA is a single warp, so the only synchronisation is
-// __syncwarp and one mbarrier for the TMA tiles.  Per job:
-//   R  64 row FFTs (2 per lane) of z = a + i b                       -> smem M  [W][W+1] float2
-//   C  per lane one column pair (k, W-k): 2 column FFTs, spectrum separation fused with the
-//      conjugate product (4 conj(FA) FB), inverse column FFT        -> smem Q  [W][W/2+1] float2
-//   I  per lane two Hermitian rows packed into one inverse FFT      -> 2 rows of the map in regs
-//   E  min / argmax / neighbours / second peak on the shifted map   -> u, v, mask
-// The next job's tiles are requested (TMA) right after phase R has consumed the current ones.
+// Execution model: persistent CTAs (one per SM) of NWARPS independent warps.  A warp owns a "job" of
+// NW = 64 / W interrogation windows (W = 64/32/16); H = W/2 lanes work on one window and every lane
+// runs exactly one W-point complex FFT per phase, entirely in registers:
+//   Ra  rows (l, l+H) of frame a packed as z = row_l + i row_{l+H}; FFT; the two real-row spectra are
+//       separated in registers and their half spectra (bins 0..H, bins 0 and H packed into one
+//       complex number) go to the exchange buffer X [W][H] in shared memory
+//   Ca  lane l transforms column l of X -> A^[.][l]; the spectrum is PARKED in tensor memory (TMEM is
+//       lane-private scratch here: tcgen05.st / tcgen05.ld, no MMA), which frees both the registers
+//       and the exchange buffer
+//   Rb  same as Ra for frame b (its tile is fetched by TMA while Ca computes)
+//   Cb  column FFT of b, product conj(A^) B^ in place against the parked spectrum, inverse column
+//       FFT on the digit-reversed registers (FftRev: no reordering) -> Q [W][H] in the same buffer
+//   I   two Hermitian rows (l, l+H) of Q packed into one inverse FFT -> two rows of the correlation
+//       map in registers
+//   E   min / argmax / neighbours / second peak on the fft-shifted map -> u, v, mask
+// Shared memory per window is W*(H+1)*8 bytes (16.5 KB for W = 64) -- half of a complex W x W
+// buffer -- and it also receives the TMA tiles, so 12 (W=64) to 24 (W=16) warps are resident per SM.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -35,13 +43,15 @@ template <int W>
 struct Geo {
     static_assert(W == 16 || W == 32 || W == 64, "window size");
     static constexpr int NW = 64 / W;                 // windows per warp job
-    static constexpr int HALF = W / 2;                // lanes per window in phases C, I, E
+    static constexpr int HALF = W / 2;                // lanes per window
     static constexpr int LOGW = (W == 64) ? 6 : (W == 32 ? 5 : 4);
-    static constexpr int PM = W + 1;                  // pitch of M   (float2)
-    static constexpr int PQ = W / 2 + 1;              // pitch of Q   (float2)
-    static constexpr int PC = W + 1;                  // pitch of map (float)
-    static constexpr int MB = W * PM * 8;             // bytes of one window's exchange region
+    static constexpr int PX = W / 2 + 1;              // pitch of X / Q rows (float2); odd -> conflict free
+    static constexpr int PC = W + 1;                  // pitch of map rows (float)
+    static constexpr int XB = W * PX * 8;
+    static constexpr int MAPB = W * PC * 4;
+    static constexpr int REGION = (((XB > MAPB ? XB : MAPB) + 255) / 256) * 256;   // one window's buffer
     static constexpr float K = 4.0f * W * W;          // map = K * sum_x a(x) b(x+s)
+    static constexpr int TCOLS = 2 * W;               // TMEM columns (32-bit) one warp parks
 };
 
 template <int W, int LOADER>
@@ -55,9 +65,8 @@ struct Tile {
     static constexpr int BX = W + 16;                                    // box bytes per row
     static constexpr int BY = (LOADER == LD_FRAME_CWS) ? W + 1 : W;      // box rows
     static constexpr int SWZ = (BX == 32) ? 1 : 0;                       // TMA swizzle: 32B / none
-    static constexpr int ALIGN = (SWZ == 1) ? 256 : 128;
     static constexpr int TX = BX * BY;
-    static constexpr int BYTES = kFrame ? ((TX + ALIGN - 1) / ALIGN) * ALIGN : 0;
+    static_assert(!kFrame || TX <= Geo<W>::REGION, "the tile is staged inside the window's buffer");
     // byte offset of 16-byte chunk `chunk` of row `row`.  Row pitches of 80 / 48 bytes (and the
     // 32-byte swizzle for 32) make 8 consecutive rows hit 8 distinct 16-byte bank groups, so the
     // per-lane LDS.128 row reads are bank-conflict free.
@@ -91,28 +100,29 @@ __device__ __forceinline__ void load_row_words(const unsigned char* tile, int ro
     });
 }
 
+// Shared memory of one warp (all offsets relative to the warp's slot)
 template <int W, int LOADER>
 struct Smem {
     using G = Geo<W>;
     using T = Tile<W, LOADER>;
-    static constexpr int TILE_OFF = 0;
-    static constexpr int TILES = G::NW * 2 * T::BYTES;
-    static constexpr int EX_OFF = ((TILES + 127) / 128) * 128;
-    static constexpr int EX = G::NW * G::MB;
-    static constexpr int XW_OFF = EX_OFF + EX;                               // float2 [NW][2][W]
-    static constexpr int XW = (LOADER == LD_FRAME_CWS) ? G::NW * 2 * W * 8 : 0;
-    static constexpr int XF_OFF = XW_OFF + XW;                               // int    [NW][2][W]
-    static constexpr int XF = (LOADER == LD_FRAME_CWS) ? G::NW * 2 * W * 4 : 0;
-    static constexpr int TD_OFF = ((XF_OFF + XF + 15) / 16) * 16;            // TileDesc [2][NW][2]: per (window, frame), double buffered
-    static constexpr int TD = T::kFrame ? 2 * G::NW * 2 * 32 : 0;
+    static constexpr int REG_OFF = 0;                                        // NW window buffers
+    static constexpr int XW_OFF = REG_OFF + G::NW * G::REGION;               // float2 [NW][W]  (CWS column taps)
+    static constexpr int XW = (LOADER == LD_FRAME_CWS) ? G::NW * W * 8 : 0;
+    static constexpr int XF_OFF = XW_OFF + XW;                               // int    [NW][W]
+    static constexpr int XF = (LOADER == LD_FRAME_CWS) ? G::NW * W * 4 : 0;
+    static constexpr int TD_OFF = ((XF_OFF + XF + 15) / 16) * 16;            // TileDesc [NW][2]
+    static constexpr int TD = T::kFrame ? G::NW * 2 * 32 : 0;
     static constexpr int BAR_OFF = ((TD_OFF + TD + 7) / 8) * 8;
     static constexpr int TOTAL = BAR_OFF + 8;
-    // One CTA per SM made of NWARPS independent warps (each with its own STRIDE bytes of smem)
-    // that walk the phases in lock step, so the SM fetches the (large, fully unrolled) instruction
-    // stream once per CTA instead of once per warp.
     static constexpr int STRIDE = ((TOTAL + 255) / 256) * 256;
     static constexpr int SMEM_MAX = 232448;           // 227 KB opt-in limit per CTA
-    static constexpr int NWARPS = (SMEM_MAX / STRIDE) > 16 ? 16 : (SMEM_MAX / STRIDE);
+    // warps per CTA: bounded by shared memory, by the register file (launch bounds) and by the 512
+    // TMEM columns (4 lane quarters x 512 / TCOLS warps)
+    static constexpr int WARP_CAP = (W == 64) ? 12 : (W == 32 ? 16 : 24);
+    static constexpr int TMEM_CAP = 4 * (512 / G::TCOLS);
+    static constexpr int BY_SMEM = SMEM_MAX / STRIDE;
+    static constexpr int NWARPS0 = BY_SMEM < WARP_CAP ? BY_SMEM : WARP_CAP;
+    static constexpr int NWARPS = NWARPS0 < TMEM_CAP ? NWARPS0 : TMEM_CAP;
     static constexpr int CTA_BYTES = NWARPS * STRIDE;
 };
 
@@ -159,14 +169,6 @@ __device__ __forceinline__ float u8f(uint32_t word, int b) {
     return static_cast<float>((word >> (8 * b)) & 0xffu);
 }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return max(lo, min(hi, v)); }
-
-// 4 * conj(FA) * FB where FA = (X + conj(Yc)) / 2, FB = (X - conj(Yc)) / (2i): spectrum separation of
-// z = a + i b fused with the conjugate product of the reference's correalte_fft (PB:255).
-__device__ __forceinline__ float2 xcorr_bin(float2 X, float2 Yc) {
-    float re = 2.0f * fmaf(X.x, Yc.y, X.y * Yc.x);
-    float im = fmaf(Yc.x, Yc.x, Yc.y * Yc.y) - fmaf(X.x, X.x, X.y * X.y);
-    return make_float2(re, im);
-}
 
 // ----------------------------------------------------------------------------------------
 // window geometry
@@ -239,6 +241,51 @@ __device__ __forceinline__ void frame_origin(const PassParams& p, int g, const W
     }
 }
 
+
+// ----------------------------------------------------------------------------------------
+// Tensor memory as lane-private scratch (tcgen05.alloc / st / ld; 32x32b shape: thread i of a warp
+// addresses TMEM lane 32 * (warp % 4) + i, consecutive 32-bit columns)
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc_512(uint32_t smem_dst) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_dst) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_512(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 8 complex numbers = 16 columns
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float2 (&v)[8]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "f"(v[0].x), "f"(v[0].y), "f"(v[1].x), "f"(v[1].y), "f"(v[2].x), "f"(v[2].y), "f"(v[3].x),
+        "f"(v[3].y), "f"(v[4].x), "f"(v[4].y), "f"(v[5].x), "f"(v[5].y), "f"(v[6].x), "f"(v[6].y), "f"(v[7].x),
+        "f"(v[7].y)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float2 (&v)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x),
+          "=f"(v[3].y), "=f"(v[4].x), "=f"(v[4].y), "=f"(v[5].x), "=f"(v[5].y), "=f"(v[6].x), "=f"(v[6].y),
+          "=f"(v[7].x), "=f"(v[7].y)
+        : "r"(taddr)
+        : "memory");
+}
+
+// Parking order of a column spectrum: entry i of the parked array is bin park_bin<W>(i) =
+// 0, W/2, 1, W-1, 2, W-2, ...  Every aligned group of 8 entries is closed under k -> W - k, which is
+// what the lane that owns the packed real columns (0, W/2) needs to separate them chunk by chunk.
+template <int W>
+__host__ __device__ constexpr int park_bin(int i) {
+    if (i == 0) return 0;
+    if (i == 1) return W / 2;
+    return (i & 1) ? W - i / 2 : i / 2;
+}
+
 // ----------------------------------------------------------------------------------------
 // the kernel
 // ----------------------------------------------------------------------------------------
@@ -250,30 +297,46 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
     using T = Tile<W, LOADER>;
     using S = Smem<W, LOADER>;
     using F = Fft<W>;
-    constexpr int NW = G::NW, HALF = G::HALF, LOGW = G::LOGW, PM = G::PM, PQ = G::PQ, PC = G::PC;
+    using FR = FftRev<W>;
+    constexpr int NW = G::NW, HALF = G::HALF, LOGW = G::LOGW, PX = G::PX, PC = G::PC;
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr bool kTmem = (SINK != SK_WIN);
 
     extern __shared__ __align__(1024) unsigned char smem_cta[];
+    __shared__ uint32_t tmem_base_sh;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    unsigned char* smem = smem_cta + warp * S::STRIDE;       // this warp's private region
+    const int nwarps = blockDim.x >> 5;                      // <= S::NWARPS (launcher)
+    unsigned char* smem = smem_cta + warp * S::STRIDE;       // this warp's private slot
     const int n_total = static_cast<int>(p.n_total);
     const int njobs = (n_total + NW - 1) / NW;
-    const int job_stride = gridDim.x * S::NWARPS;
+    const int job_stride = gridDim.x * nwarps;
     const uint32_t bar = smem_u32(smem + S::BAR_OFF);
     uint32_t parity = 0;
     bool pending = false;
 
+    uint32_t tpark = 0;                                      // TMEM address of this warp's parking area
+    if constexpr (kTmem) {
+        if (warp == 0) tmem_alloc_512(smem_u32(&tmem_base_sh));
+        tmem_fence_before();
+        __syncthreads();
+        tmem_fence_after();
+        tpark = tmem_base_sh + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>((warp >> 2) * G::TCOLS);
+    }
     if constexpr (T::kFrame) {
         if (lane == 0) mbar_init(bar, 1);
         __syncwarp();
     }
 
-    // ---- request / gather the input tiles of one job -----------------------------------
-    // buf: which half of the double-buffered descriptor table the job uses
-    auto stage_tiles = [&](int job, int buf) {
+    const int wi = lane / HALF;            // window of this lane inside the job
+    const int l = lane % HALF;             // rows (l, l + H) in phases R and I, column l in phase C
+    unsigned char* const region = smem + S::REG_OFF + wi * G::REGION;
+    float2* const Xw = reinterpret_cast<float2*>(region);
+
+    // ---- descriptors of the (window, frame) tiles of one job ------------------------------
+    auto make_desc = [&](int job) {
         if constexpr (T::kFrame) {
-            TileDesc* desc = reinterpret_cast<TileDesc*>(smem + S::TD_OFF) + buf * (NW * 2);
+            TileDesc* desc = reinterpret_cast<TileDesc*>(smem + S::TD_OFF);
             if (lane < NW * 2) {
                 const int q = lane, frame = q & 1;
                 const int g = min(job * NW + (q >> 1), n_total - 1);
@@ -289,17 +352,27 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                 desc[q] = dsc;
             }
             __syncwarp();
+        }
+    };
+
+    // ---- bring the tiles of `frame` into the (currently dead) window buffers ----------------
+    auto stage_issue = [&](int frame) {
+        if constexpr (T::kFrame) {
+            TileDesc* desc = reinterpret_cast<TileDesc*>(smem + S::TD_OFF);
+            fence_proxy_async();            // generic accesses to the buffers are ordered before the TMA writes
+            __syncwarp();
             uint32_t tx = 0;
 #pragma unroll 1
-            for (int q = 0; q < NW * 2; ++q) {
+            for (int w2 = 0; w2 < NW; ++w2) {
+                const int q = w2 * 2 + frame;
                 const TileDesc dsc = desc[q];
                 if (dsc.d >= 0) {
                     tx += T::TX;
                 } else {
                     // border window: the reference addresses taps by FLAT index clamped to
                     // [0, H*W-1] (PB:172-180, 213-214), i.e. columns wrap into neighbouring rows.
-                    const unsigned char* f = ((q & 1) ? p.fb : p.fa) + dsc.pair * p.pair_stride;
-                    unsigned char* tile = smem + S::TILE_OFF + q * T::BYTES;
+                    const unsigned char* f = (frame ? p.fb : p.fa) + dsc.pair * p.pair_stride;
+                    unsigned char* tile = smem + S::REG_OFF + w2 * G::REGION;
                     const int last_y = p.H - 1, last_x = p.Wf - 1;
 #pragma unroll 4
                     for (int e = lane; e < T::BY * T::USED; e += 32) {
@@ -324,35 +397,24 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
             }
             if (tx != 0) {
                 if (lane == 0) {
-                    fence_proxy_async();
                     mbar_arrive_expect_tx(bar, tx);
 #pragma unroll 1
-                    for (int q = 0; q < NW * 2; ++q) {
-                        const TileDesc dsc = desc[q];
+                    for (int w2 = 0; w2 < NW; ++w2) {
+                        const TileDesc dsc = desc[w2 * 2 + frame];
                         if (dsc.d >= 0)
-                            tma_load_3d(smem_u32(smem + S::TILE_OFF + q * T::BYTES), (q & 1) ? &tmB : &tmA,
-                                        bar, dsc.ox & ~15, dsc.oy, dsc.pair);
+                            tma_load_3d(smem_u32(smem + S::REG_OFF + w2 * G::REGION), frame ? &tmB : &tmA, bar,
+                                        dsc.ox & ~15, dsc.oy, dsc.pair);
                     }
                 }
                 pending = true;
             }
             __syncwarp();
             // gathered tiles are stored from byte 0
-            if (lane < NW * 2 && desc[lane].d < 0) desc[lane].d = 0;
+            if (lane < NW && desc[lane * 2 + frame].d < 0) desc[lane * 2 + frame].d = 0;
             __syncwarp();
         }
     };
-
-    // every warp of the CTA runs the same number of iterations (block barriers inside); a warp
-    // without work re-does the last job and suppresses its output (n_total guard via `active`)
-    int job = blockIdx.x * S::NWARPS + warp;
-    int buf = 0;
-    stage_tiles(min(job, njobs - 1), buf);
-
-    for (int base = blockIdx.x * S::NWARPS; base < njobs; base += job_stride, job += job_stride, buf ^= 1) {
-        const bool active = job < njobs;
-        const int job_c = min(job, njobs - 1);
-        if (p.sync_mask & 64) __syncthreads();
+    auto stage_wait = [&]() {
         if constexpr (T::kFrame) {
             if (pending) {
                 mbar_wait(bar, parity);
@@ -360,88 +422,68 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                 pending = false;
             }
         }
+    };
 
-        // ---- CWS: per-column tap descriptors (shared by all rows of a window) ------------
-        bool anyflag = false;
-        if constexpr (LOADER == LD_FRAME_CWS) {
-            float2* xw = reinterpret_cast<float2*>(smem + S::XW_OFF);
-            int* xf = reinterpret_cast<int*>(smem + S::XF_OFF);
-            bool flag = false;
-            const TileDesc* desc = reinterpret_cast<const TileDesc*>(smem + S::TD_OFF) + buf * (NW * 2);
-#pragma unroll
-            for (int e = lane; e < NW * 2 * W; e += 32) {
-                const int j = e & (W - 1), q = e >> LOGW;      // q = wi*2 + frame
-                const TileDesc dsc = desc[q];
-                const AxisTap cx = cws_axis(dsc.c0 + j, dsc.vx);
-                xw[e] = make_float2(cx.w1, cx.w0);
-                xf[e] = (cx.exact ? 2 : 0) | ((cx.lo - (dsc.ox + j)) & 1);
-                flag |= cx.exact;
-                // rows: every row index appears as some j (square windows) -> same loop covers them
-                const AxisTap cy = cws_axis(dsc.r0 + j, dsc.vy);
-                flag |= cy.exact;
-            }
-            anyflag = __any_sync(FULL, flag);
-            __syncwarp();
-        }
-
-        // ===================================================================================
-        // Six FFT steps per lane around ONE shared transform body (the unrolled W-point FFT is the
-        // bulk of the code; sharing it keeps every phase's working set inside the instruction cache):
-        //   s = 0, 1  row FFTs of z = a + i b                  (phase R)  -> M
-        //   s = 2, 3  forward FFTs of the column pair (k, W-k) (phase C)
-        //   s = 4     inverse column FFT of the product        (phase C)  -> Q
-        //   s = 5     inverse FFT of two packed Hermitian rows (phase I)  -> map rows in registers
-        // ===================================================================================
-        const int wi = lane / HALF;            // window of this lane in phases C, I, E
-        const int kc = lane % HALF;            // column pair (kc, W-kc); kc == 0: columns 0 and W/2
-        const int l = kc;                      // rows l and l + W/2 in phase I
-        const int col1 = kc, col2 = kc ? W - kc : HALF;
-        float2* const Mw = reinterpret_cast<float2*>(smem + S::EX_OFF + wi * G::MB);
-        float sum_a = 0.f, sum_b = 0.f;        // pixel sums of the window (valid in lanes kc == 0)
-        // bit w set: window w of the job is exactly constant in frame a (b).  The reference then gets
-        // an exactly constant correlation map (all ties -> peak index 0, ratio 1); packing a + i b
-        // into one transform would leak ~1e-7 of the other frame into it, so such windows are
-        // detected here and their map is forced to zero.
-        unsigned const_a = 0xffffffffu, const_b = 0xffffffffu;
-        float lead_a = 0.f, lead_b = 0.f;
-        float2 x[W];                           // the FFT operand
-        float2 xs[(W <= 32) ? W : 1];          // W <= 32: spectrum of column k kept while column W-k is transformed
-        constexpr int NSTEP = (SINK == SK_WIN) ? 2 : 6;
 #pragma unroll 1
-        for (int s = 0; s < NSTEP; ++s) {
-            if ((p.sync_mask >> s) & 1) __syncthreads();        // lock step: shared instruction fetch
+    for (int job = blockIdx.x * nwarps + warp; job < njobs; job += job_stride) {
+        const int g = min(job * NW + wi, n_total - 1);       // window of this lane (clamped: the last job may be ragged)
+        const bool g_valid = job * NW + wi < n_total;
+        make_desc(job);
+        stage_issue(0);
+
+        float sum_a = 0.f, sum_b = 0.f;        // pixel sums of the window (valid in lanes l == 0)
+        float2 x[W];                           // the FFT operand
+        // ===================================================================================
+        // Five FFT steps per lane around ONE shared transform body:
+        //   s = 0  Ra    s = 1  Ca (+ park)    s = 2  Rb    s = 3  Cb (+ product, inverse, -> Q)    s = 4  I
+        // ===================================================================================
+#pragma unroll 1
+        for (int s = 0; s < 5; ++s) {
             // ---------------------------------------------------------------- load
-            const int grow = lane + 32 * s;
-            const int rwi = (grow >> LOGW) & (NW - 1), rt = grow & (W - 1);     // row mapping (s < 2)
-            const int g = min(job_c * NW + rwi, n_total - 1);
-            if (s < 2) {
+            if (s == 0 || s == 2) {
+                const int frame = s >> 1;
+                stage_wait();
                 if constexpr (LOADER == LD_FRAME_INT) {
-                    const unsigned char* ta = smem + S::TILE_OFF + (rwi * 2) * T::BYTES;
-                    const unsigned char* tb = ta + T::BYTES;
-                    const TileDesc* desc = reinterpret_cast<const TileDesc*>(smem + S::TD_OFF) + buf * (NW * 2);
-                    uint32_t wa[W / 4], wb[W / 4];
-                    load_row_words<W, LOADER, W / 4>(ta, rt, desc[rwi * 2].d, wa);
-                    load_row_words<W, LOADER, W / 4>(tb, rt, desc[rwi * 2 + 1].d, wb);
+                    const TileDesc* desc = reinterpret_cast<const TileDesc*>(smem + S::TD_OFF);
+                    const int d = desc[wi * 2 + frame].d;
+                    uint32_t w0[W / 4], w1[W / 4];
+                    load_row_words<W, LOADER, W / 4>(region, l, d, w0);
+                    load_row_words<W, LOADER, W / 4>(region, l + HALF, d, w1);
                     static_for<0, W>([&](auto jc) {
                         constexpr int j = decltype(jc)::value;
-                        x[j] = make_float2(u8f(wa[j >> 2], j & 3), u8f(wb[j >> 2], j & 3));
+                        x[j] = make_float2(u8f(w0[j >> 2], j & 3), u8f(w1[j >> 2], j & 3));
                     });
                 } else if constexpr (LOADER == LD_FRAME_CWS) {
-                    const TileDesc* desc = reinterpret_cast<const TileDesc*>(smem + S::TD_OFF) + buf * (NW * 2);
-                    const float2* xw = reinterpret_cast<const float2*>(smem + S::XW_OFF);
-                    const int* xf = reinterpret_cast<const int*>(smem + S::XF_OFF);
-                    static_for<0, 2>([&](auto fc) {
-                        constexpr int frame = decltype(fc)::value;
-                        const TileDesc dsc = desc[rwi * 2 + frame];
+                    const TileDesc* desc = reinterpret_cast<const TileDesc*>(smem + S::TD_OFF);
+                    float2* xw = reinterpret_cast<float2*>(smem + S::XW_OFF);
+                    int* xf = reinterpret_cast<int*>(smem + S::XF_OFF);
+                    // per-column tap descriptors of this frame (shared by all rows of a window)
+                    bool flag = false;
+#pragma unroll
+                    for (int e = lane; e < NW * W; e += 32) {
+                        const int j = e & (W - 1), w2 = e >> LOGW;
+                        const TileDesc dsc = desc[w2 * 2 + frame];
+                        const AxisTap cx = cws_axis(dsc.c0 + j, dsc.vx);
+                        xw[e] = make_float2(cx.w1, cx.w0);
+                        xf[e] = (cx.exact ? 2 : 0) | ((cx.lo - (dsc.ox + j)) & 1);
+                        flag |= cx.exact;
+                        // rows: every row index appears as some j (square windows) -> same loop covers them
+                        const AxisTap cy = cws_axis(dsc.r0 + j, dsc.vy);
+                        flag |= cy.exact;
+                    }
+                    const bool anyflag = __any_sync(FULL, flag);
+                    __syncwarp();
+                    const TileDesc dsc = desc[wi * 2 + frame];
+                    const float2* xwq = xw + wi * W;
+                    const int* xfq = xf + wi * W;
+                    static_for<0, 2>([&](auto hc) {
+                        constexpr int half = decltype(hc)::value;
+                        const int rt = l + half * HALF;
                         const AxisTap cy = cws_axis(dsc.r0 + rt, dsc.vy);
                         const int jy = (cy.lo - (dsc.oy + rt)) & 1;
-                        const unsigned char* tile = smem + S::TILE_OFF + (rwi * 2 + frame) * T::BYTES;
-                        const int d = dsc.d;
                         uint32_t r0w[W / 4 + 1], r1w[W / 4 + 1];
-                        load_row_words<W, LOADER, W / 4 + 1>(tile, rt, d, r0w);
-                        load_row_words<W, LOADER, W / 4 + 1>(tile, rt + 1, d, r1w);
-                        const float2* xwq = xw + (rwi * 2 + frame) * W;
-                        const int* xfq = xf + (rwi * 2 + frame) * W;
+                        load_row_words<W, LOADER, W / 4 + 1>(region, rt, dsc.d, r0w);
+                        load_row_words<W, LOADER, W / 4 + 1>(region, rt + 1, dsc.d, r1w);
                         float l0 = u8f(r0w[0], 0), l1 = u8f(r1w[0], 0);
                         if (!anyflag) {
                             static_for<0, W>([&](auto jc) {
@@ -454,7 +496,7 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                                 acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(h0, wx.y), cy.w1));
                                 acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(l1, wx.x), cy.w0));
                                 acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(h1, wx.y), cy.w0));
-                                if constexpr (frame == 0) x[j].x = acc; else x[j].y = acc;
+                                if constexpr (half == 0) x[j].x = acc; else x[j].y = acc;
                                 l0 = h0; l1 = h1;
                             });
                         } else {
@@ -472,32 +514,30 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                                 const float s0 = (fl & 1) ? h0 : l0, s1 = (fl & 1) ? h1 : l1;
                                 const float q11 = jy ? s1 : s0;
                                 acc = ((fl & 2) || cy.exact) ? q11 : acc;
-                                if constexpr (frame == 0) x[j].x = acc; else x[j].y = acc;
+                                if constexpr (half == 0) x[j].x = acc; else x[j].y = acc;
                                 l0 = h0; l1 = h1;
                             });
                         }
                     });
                 } else if constexpr (LOADER == LD_EXPL_F32) {
-                    const float4* ra = reinterpret_cast<const float4*>(
-                        static_cast<const float*>(p.wa) + (static_cast<long long>(g) * W + rt) * W);
-                    const float4* rb = reinterpret_cast<const float4*>(
-                        static_cast<const float*>(p.wb) + (static_cast<long long>(g) * W + rt) * W);
+                    const float* base = static_cast<const float*>(frame ? p.wb : p.wa) + static_cast<long long>(g) * W * W;
+                    const float4* r0 = reinterpret_cast<const float4*>(base + l * W);
+                    const float4* r1 = reinterpret_cast<const float4*>(base + (l + HALF) * W);
                     static_for<0, W / 4>([&](auto cc) {
                         constexpr int c = decltype(cc)::value;
-                        const float4 va = __ldg(ra + c), vb = __ldg(rb + c);
+                        const float4 va = __ldg(r0 + c), vb = __ldg(r1 + c);
                         x[4 * c] = make_float2(va.x, vb.x);
                         x[4 * c + 1] = make_float2(va.y, vb.y);
                         x[4 * c + 2] = make_float2(va.z, vb.z);
                         x[4 * c + 3] = make_float2(va.w, vb.w);
                     });
                 } else {
-                    const uint4* ra = reinterpret_cast<const uint4*>(
-                        static_cast<const unsigned char*>(p.wa) + (static_cast<long long>(g) * W + rt) * W);
-                    const uint4* rb = reinterpret_cast<const uint4*>(
-                        static_cast<const unsigned char*>(p.wb) + (static_cast<long long>(g) * W + rt) * W);
+                    const unsigned char* base = static_cast<const unsigned char*>(frame ? p.wb : p.wa) + static_cast<long long>(g) * W * W;
+                    const uint4* r0 = reinterpret_cast<const uint4*>(base + l * W);
+                    const uint4* r1 = reinterpret_cast<const uint4*>(base + (l + HALF) * W);
                     static_for<0, W / 16>([&](auto cc) {
                         constexpr int c = decltype(cc)::value;
-                        const uint4 qa = __ldg(ra + c), qb = __ldg(rb + c);
+                        const uint4 qa = __ldg(r0 + c), qb = __ldg(r1 + c);
                         const uint32_t wa[4] = {qa.x, qa.y, qa.z, qa.w};
                         const uint32_t wb[4] = {qb.x, qb.y, qb.z, qb.w};
                         static_for<0, 16>([&](auto bc) {
@@ -506,144 +546,144 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                         });
                     });
                 }
+                __syncwarp();                   // tiles fully read before X overwrites the buffer
 
-            } else if (s == 2) {
-                static_for<0, W>([&](auto tc) { constexpr int t = decltype(tc)::value; x[t] = Mw[t * PM + col1]; });
-            } else if (s == 3) {
-                static_for<0, W>([&](auto tc) { constexpr int t = decltype(tc)::value; x[t] = Mw[t * PM + col2]; });
-            } else if (s == 5) {
+                if constexpr (SINK == SK_WIN) {
+                    if (g_valid) {
+                        float* dst = (frame ? p.win_b_out : p.win_a_out) + static_cast<long long>(g) * W * W;
+                        float4* o0 = reinterpret_cast<float4*>(dst + l * W);
+                        float4* o1 = reinterpret_cast<float4*>(dst + (l + HALF) * W);
+                        static_for<0, W / 4>([&](auto cc) {
+                            constexpr int c = decltype(cc)::value;
+                            o0[c] = make_float4(x[4 * c].x, x[4 * c + 1].x, x[4 * c + 2].x, x[4 * c + 3].x);
+                            o1[c] = make_float4(x[4 * c].y, x[4 * c + 1].y, x[4 * c + 2].y, x[4 * c + 3].y);
+                        });
+                    }
+                    if (s == 0) stage_issue(1);
+                    ++s;                        // no transforms: skip the column step
+                    continue;
+                }
+            } else if (s == 1 || s == 3) {
+                static_for<0, W>([&](auto tc) { constexpr int t = decltype(tc)::value; x[t] = Xw[t * PX + l]; });
+                __syncwarp();                   // X fully read: the buffer is dead
+                if (s == 1) stage_issue(1);     // frame b tiles arrive while column a is transformed
+            } else {
                 // two Hermitian rows l, l + W/2 of Q packed into one complex inverse FFT
-                const float2* Qw = Mw;
-                const float2 a0 = Qw[l * PQ], b0 = Qw[(l + HALF) * PQ];
+                const float2 a0 = Xw[l * PX], b0 = Xw[(l + HALF) * PX];
                 x[0] = make_float2(b0.x, a0.x);
                 x[HALF] = make_float2(b0.y, a0.y);
                 static_for<1, HALF>([&](auto kc_) {
                     constexpr int k = decltype(kc_)::value;
-                    const float2 R1 = Qw[l * PQ + k], R2 = Qw[(l + HALF) * PQ + k];
+                    const float2 R1 = Xw[l * PX + k], R2 = Xw[(l + HALF) * PX + k];
                     x[k] = make_float2(R1.y + R2.x, R1.x - R2.y);
                     x[W - k] = make_float2(R2.x - R1.y, R1.x + R2.y);
                 });
                 __syncwarp();                   // Q fully read before the map overwrites it
             }
 
-            if (s < 2 && SINK == SK_DISP) {
-                uint32_t da = 0u, db = 0u;
-                static_for<1, W>([&](auto jc) {
-                    constexpr int j = decltype(jc)::value;
-                    da |= __float_as_uint(x[j].x) ^ __float_as_uint(x[0].x);
-                    db |= __float_as_uint(x[j].y) ^ __float_as_uint(x[0].y);
-                });
-                constexpr int SEG = (W < 32) ? W : 32;             // lanes holding rows of one window
-                const int seg_lane0 = lane & ~(SEG - 1);
-                // first pixel of the window: row 0 is read in step 0 for W = 64, in this step otherwise
-                if (W < 64 || s == 0) {
-                    lead_a = __shfl_sync(FULL, x[0].x, seg_lane0);
-                    lead_b = __shfl_sync(FULL, x[0].y, seg_lane0);
-                }
-                const unsigned oka = __ballot_sync(FULL, da == 0u && x[0].x == lead_a);
-                const unsigned okb = __ballot_sync(FULL, db == 0u && x[0].y == lead_b);
-#pragma unroll
-                for (int k = 0; k < 32 / SEG; ++k) {
-                    const unsigned segmask = (SEG == 32) ? 0xffffffffu : (((1u << SEG) - 1u) << (k * SEG));
-                    const int wdx = ((32 * s + k * SEG) >> LOGW) & (NW - 1);
-                    if ((oka & segmask) != segmask) const_a &= ~(1u << wdx);
-                    if ((okb & segmask) != segmask) const_b &= ~(1u << wdx);
-                }
-            }
-
-            if constexpr (SINK == SK_WIN) {
-                if (active && job_c * NW + rwi < n_total) {
-                    float4* oa = reinterpret_cast<float4*>(p.win_a_out + (static_cast<long long>(g) * W + rt) * W);
-                    float4* ob = reinterpret_cast<float4*>(p.win_b_out + (static_cast<long long>(g) * W + rt) * W);
-                    static_for<0, W / 4>([&](auto cc) {
-                        constexpr int c = decltype(cc)::value;
-                        oa[c] = make_float4(x[4 * c].x, x[4 * c + 1].x, x[4 * c + 2].x, x[4 * c + 3].x);
-                        ob[c] = make_float4(x[4 * c].y, x[4 * c + 1].y, x[4 * c + 2].y, x[4 * c + 3].y);
-                    });
-                }
-                if (s == 1) {
-                    __syncwarp();
-                    if (base + job_stride < njobs) stage_tiles(min(job + job_stride, njobs - 1), buf ^ 1);
-                }
-                continue;
-            }
-
-            F::run(x);
+            if constexpr (SINK != SK_WIN) F::run(x);
 
             // ---------------------------------------------------------------- store
-            if (s < 2) {
-                float2* Mrow = reinterpret_cast<float2*>(smem + S::EX_OFF + rwi * G::MB) + rt * PM;
-                static_for<0, W>([&](auto kc_) {
+            if (s == 0 || s == 2) {
+                // z = r1 + i r2: R1[k] = Z[k] + conj Z[W-k], R2[k] = -i (Z[k] - conj Z[W-k])  (x2, folded into K);
+                // bins 0 and W/2 are real and share one complex slot
+                float2* X1 = Xw + l * PX;
+                float2* X2 = Xw + (l + HALF) * PX;
+                const float2 z0 = x[F::pos(0)], zh = x[F::pos(HALF)];
+                X1[0] = make_float2(2.0f * z0.x, 2.0f * zh.x);
+                X2[0] = make_float2(2.0f * z0.y, 2.0f * zh.y);
+                static_for<1, HALF>([&](auto kc_) {
                     constexpr int k = decltype(kc_)::value;
-                    Mrow[k] = x[F::pos(k)];
-                });
-                if (s == 1) {
-                    __syncwarp();
-                    // tiles are consumed: request the next job's while this one is transformed
-                    if (base + job_stride < njobs) stage_tiles(min(job + job_stride, njobs - 1), buf ^ 1);
-                }
-            } else if (s == 2) {
-                if constexpr (W <= 32) {
-                    static_for<0, W>([&](auto ic) { constexpr int i = decltype(ic)::value; xs[i] = x[i]; });
-                } else {
-                    // W == 64: two 64-point spectra do not fit in registers; X is parked in its own
-                    // (lane-private) column of M, natural order, and streamed back during the product
-                    static_for<0, W>([&](auto rc) { constexpr int r = decltype(rc)::value; Mw[r * PM + col1] = x[F::pos(r)]; });
-                }
-            } else if (s == 3) {
-                // x = spectrum Y of column W-k; X = spectrum of column k.  Product, (im, re) swapped
-                // for the inverse transform, written back into x.
-                auto Xn = [&](auto rc) -> float2 {
-                    constexpr int r = decltype(rc)::value;
-                    if constexpr (W <= 32) return xs[F::pos(r)];
-                    else return Mw[r * PM + col1];
-                };
-                float2 pq[W];
-                if (kc != 0) {
-                    static_for<0, W>([&](auto rc) {
-                        constexpr int r = decltype(rc)::value;
-                        const float2 P = xcorr_bin(Xn(rc), x[F::pos((W - r) % W)]);
-                        pq[r] = make_float2(P.y, P.x);
-                    });
-                } else {
-                    const float2 dc = Xn(std::integral_constant<int, 0>{});
-                    sum_a = dc.x;
-                    sum_b = dc.y;
-                    static_for<0, HALF + 1>([&](auto rc) {
-                        constexpr int r = decltype(rc)::value;
-                        constexpr int nr = (W - r) % W;
-                        float2 P0 = xcorr_bin(Xn(rc), Xn(std::integral_constant<int, nr>{}));
-                        const float2 Ph = xcorr_bin(x[F::pos(r)], x[F::pos(nr)]);
-                        // drop the DC bin (mean product): a constant that `- amin` removes anyway
-                        if constexpr (r == 0 && SINK == SK_DISP) P0 = make_float2(0.f, 0.f);
-                        // out[r] = P0 + i Ph ; out[-r] = conj(P0) + i conj(Ph); stored (im, re)
-                        pq[r] = make_float2(P0.y + Ph.x, P0.x - Ph.y);
-                        if constexpr (nr != r) pq[nr] = make_float2(Ph.x - P0.y, P0.x + Ph.y);
-                    });
-                }
-                static_for<0, W>([&](auto ic) { constexpr int i = decltype(ic)::value; x[i] = pq[i]; });
-            } else if (s == 4) {
-                __syncwarp();                  // M (and the parked X) fully read before Q overwrites it
-                float2* Qw = Mw;
-                static_for<0, W>([&](auto tc) {
-                    constexpr int t = decltype(tc)::value;
-                    const float2 o = x[F::pos(t)];
-                    Qw[t * PQ + kc] = make_float2(o.y, o.x);
+                    const float2 zk = x[F::pos(k)], zn = x[F::pos(W - k)];
+                    X1[k] = make_float2(zk.x + zn.x, zk.y - zn.y);
+                    X2[k] = make_float2(zk.y + zn.y, zn.x - zk.x);
                 });
                 __syncwarp();
+            } else if (s == 1) {
+                if constexpr (kTmem) {
+                    static_for<0, W / 8>([&](auto cc) {
+                        constexpr int c = decltype(cc)::value;
+                        float2 v[8];
+                        static_for<0, 8>([&](auto ic) {
+                            constexpr int i = decltype(ic)::value;
+                            v[i] = x[F::pos(park_bin<W>(8 * c + i))];
+                        });
+                        tmem_st8(tpark + 16 * c, v);
+                    });
+                    tmem_wait_st();
+                }
+            } else if (s == 3) {
+                if constexpr (kTmem) {
+                    static_for<0, W / 8>([&](auto cc) {
+                        constexpr int c = decltype(cc)::value;
+                        float2 A[8];
+                        tmem_ld8(tpark + 16 * c, A);
+                        tmem_wait_ld();
+                        if (l != 0) {
+                            // P = conj(A^) B^, stored (im, re) for the inverse transform
+                            static_for<0, 8>([&](auto ic) {
+                                constexpr int i = decltype(ic)::value;
+                                constexpr int sl = F::pos(park_bin<W>(8 * c + i));
+                                const float2 B = x[sl];
+                                x[sl] = make_float2(fmaf(A[i].x, B.y, -A[i].y * B.x), fmaf(A[i].x, B.x, A[i].y * B.y));
+                            });
+                        } else {
+                            // packed real columns 0 and W/2: C = c0^ + i cH^.  Separate, multiply, re-pack.
+                            static_for<0, 4>([&](auto mc) {
+                                constexpr int m = decltype(mc)::value;
+                                constexpr int i0 = 8 * c + 2 * m;
+                                if constexpr (i0 == 0) {
+                                    // bins 0 and W/2 are their own partners: everything is real
+                                    static_for<0, 2>([&](auto ec) {
+                                        constexpr int e = decltype(ec)::value;
+                                        constexpr int sl = F::pos(park_bin<W>(e));
+                                        const float2 B = x[sl];
+                                        float p0 = A[e].x * B.x;
+                                        const float ph = A[e].y * B.y;
+                                        if constexpr (e == 0) {
+                                            sum_a = 0.5f * A[e].x;
+                                            sum_b = 0.5f * B.x;
+                                            // drop the DC bin (mean product): a constant that `- amin` removes anyway
+                                            if constexpr (SINK == SK_DISP) p0 = 0.f;
+                                        }
+                                        x[sl] = make_float2(ph, p0);
+                                    });
+                                } else {
+                                    constexpr int sq = F::pos(park_bin<W>(i0)), sn = F::pos(park_bin<W>(i0 + 1));
+                                    const float2 Aq = A[2 * m], An = A[2 * m + 1], Bq = x[sq], Bn = x[sn];
+                                    const float2 a0 = make_float2(Aq.x + An.x, Aq.y - An.y);      // 2 c0^[q]
+                                    const float2 ah = make_float2(Aq.y + An.y, An.x - Aq.x);      // 2 cH^[q]
+                                    const float2 b0 = make_float2(0.25f * (Bq.x + Bn.x), 0.25f * (Bq.y - Bn.y));
+                                    const float2 bh = make_float2(0.25f * (Bq.y + Bn.y), 0.25f * (Bn.x - Bq.x));
+                                    const float2 P0 = make_float2(fmaf(a0.x, b0.x, a0.y * b0.y), fmaf(a0.x, b0.y, -a0.y * b0.x));
+                                    const float2 Ph = make_float2(fmaf(ah.x, bh.x, ah.y * bh.y), fmaf(ah.x, bh.y, -ah.y * bh.x));
+                                    // V[q] = P0 + i Ph, V[W-q] = conj(P0) + i conj(Ph); stored (im, re)
+                                    x[sq] = make_float2(P0.y + Ph.x, P0.x - Ph.y);
+                                    x[sn] = make_float2(Ph.x - P0.y, P0.x + Ph.y);
+                                }
+                            });
+                        }
+                        __syncwarp();
+                    });
+                    FR::run(x);
+                    static_for<0, W>([&](auto tc) {
+                        constexpr int t = decltype(tc)::value;
+                        const float2 o = x[FR::slot(t)];
+                        Xw[t * PX + l] = make_float2(o.y, o.x);
+                    });
+                    __syncwarp();
+                }
             }
         }
         if constexpr (SINK == SK_WIN) continue;
 
         // raw row l -> shifted row l + W/2 (values x[].y); raw row l + W/2 -> shifted row l (x[].x)
-        float* mapw = reinterpret_cast<float*>(smem + S::EX_OFF + wi * G::MB);
+        float* mapw = reinterpret_cast<float*>(region);
         float mx_hi = -FLT_MAX, mx_lo = -FLT_MAX, mn = FLT_MAX;     // hi: shifted row l + HALF
-        const bool degenerate = ((const_a | const_b) >> wi) & 1u;
         static_for<0, W>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
             constexpr int sc = (j + HALF) % W;
-            float2 o = x[F::pos(j)];
-            if (SINK == SK_DISP && degenerate) o = make_float2(0.f, 0.f);
+            const float2 o = x[F::pos(j)];
             mapw[(l + HALF) * PC + sc] = o.y;
             mapw[l * PC + sc] = o.x;
             mx_hi = fmaxf(mx_hi, o.y);
@@ -655,10 +695,10 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
         if constexpr (SINK == SK_CORR) {
 #pragma unroll 1
             for (int w2 = 0; w2 < NW; ++w2) {
-                const int g = job_c * NW + w2;
-                if (!active || g >= n_total) break;
-                const float* mw = reinterpret_cast<const float*>(smem + S::EX_OFF + w2 * G::MB);
-                float* out = p.corr_out + static_cast<long long>(g) * W * W;
+                const int g2 = job * NW + w2;
+                if (g2 >= n_total) break;
+                const float* mw = reinterpret_cast<const float*>(smem + S::REG_OFF + w2 * G::REGION);
+                float* out = p.corr_out + static_cast<long long>(g2) * W * W;
                 for (int e = lane; e < W * W; e += 32)
                     out[e] = mw[(e >> LOGW) * PC + (e & (W - 1))] * (1.0f / G::K);
             }
@@ -717,9 +757,9 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                 // row maxima from registers; the <= 8 candidate rows are rescanned from smem.
                 const int lo_f = m - 3 - 3 * W, hi_f = m + 3 + 3 * W;
                 const int ra = max(lo_f, 0) >> LOGW, rb = min(hi_f, N2 - 1) >> LOGW;
-                float s = -FLT_MAX;
-                if (l < ra || l > rb) s = fmaxf(s, mx_lo);
-                if (l + HALF < ra || l + HALF > rb) s = fmaxf(s, mx_hi);
+                float sp = -FLT_MAX;
+                if (l < ra || l > rb) sp = fmaxf(sp, mx_lo);
+                if (l + HALF < ra || l + HALF > rb) sp = fmaxf(sp, mx_hi);
                 for (int rr = ra; rr <= rb; ++rr) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -728,12 +768,12 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                         const int e = f - lo_f;                     // (i+3) + W (j+3)
                         bool in_patch = (e >= 0) && ((e & (W - 1)) <= 6) && ((e >> LOGW) <= 6);
                         in_patch |= (f == 0 && lo_f <= 0) || (f == N2 - 1 && hi_f >= N2 - 1);
-                        if (!in_patch) s = fmaxf(s, mapw[rr * PC + cc]);
+                        if (!in_patch) sp = fmaxf(sp, mapw[rr * PC + cc]);
                     }
                 }
 #pragma unroll
-                for (int o = HALF / 2; o > 0; o >>= 1) s = fmaxf(s, __shfl_xor_sync(FULL, s, o));
-                const double c2 = (static_cast<double>(s) - dmin) + eps;
+                for (int o = HALF / 2; o > 0; o >>= 1) sp = fmaxf(sp, __shfl_xor_sync(FULL, sp, o));
+                const double c2 = (static_cast<double>(sp) - dmin) + eps;
                 const double rt = cm / c2;
                 invalid = rt < p.val_ratio;
                 ratio = static_cast<float>(rt);
@@ -745,8 +785,7 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                 invalid = false;
                 ratio = 0.f;
             }
-            const int g = job_c * NW + wi;
-            if (active && l == 0 && g < n_total) {
+            if (l == 0 && g_valid) {
                 double uo = du + (p.base_u ? p.base_u[g] : 0.0);
                 double vo = dv + (p.base_v ? p.base_v[g] : 0.0);
                 if (p.pred_u) {
@@ -762,6 +801,12 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
             }
             __syncwarp();
         }
+    }
+
+    if constexpr (kTmem) {
+        tmem_fence_before();
+        __syncthreads();
+        if (warp == 0) tmem_dealloc_512(tmem_base_sh);
     }
 }
 
