@@ -96,8 +96,21 @@ def check_field(got_u, got_v, got_m, ref_u, ref_v, ref_m, corr, tight=2e-5):
 
 
 # ------------------------------------------------------------------------------------------
-# window extraction / shifting: bit-exact
+# window extraction / shifting: bit-exact for unshifted and integer-shifted (DWS) windows.  The fused
+# CWS loader evaluates the reference's four-term bilinear sum in its separable form (horizontal tap
+# shared by two rows, then the vertical tap): same value up to FP32 rounding, so those windows are
+# compared with an absolute tolerance of 2^-14 grey levels (values are 0..255; observed <= 4e-5).
+# The function-level biliniar_interpolation_CWS stays bit-exact (test_reference_layout_shift_functions).
 # ------------------------------------------------------------------------------------------
+CWS_WINDOW_ATOL = 2.0 ** -14
+
+
+def assert_cws_windows(got, ref):
+    assert got.shape == ref.shape and got.dtype == ref.dtype
+    err = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+    assert err.max() <= CWS_WINDOW_ATOL, f"max |window - reference| = {err.max():.3e}"
+
+
 @pytest.mark.parametrize("w,o", cases.PASS1_GEOMS + [(16, 12), (64, 60)])
 def test_windows_unshifted_bit_exact(G, w, o):
     a, b = cases.small_pair(seed=1)
@@ -107,16 +120,17 @@ def test_windows_unshifted_bit_exact(G, w, o):
 
 
 @pytest.mark.parametrize("w,o", [(32, 16), (16, 8), (64, 32)])
-def test_windows_shifted_bit_exact(G, golden, w, o):
+def test_windows_shifted(G, golden, w, o):
     """TMA tiles + in-register realignment + border gathers vs the reference's flat-index
     arithmetic: out-of-frame shifts, exact integers, one ulp below an integer."""
     g = golden("shift.npz")
     fr, vx, vy = cases.shift_case(seed=w, w=w, ovl=o)
     idx = O.window_index_grid(fr.shape, w, o)
     wa, wb = G.windows(fr, fr, w, o, "CWS", vx, vy)
-    assert np.array_equal(wa, O.bilinear_interpolation_cws(fr, idx, -vx[:, None, None], -vy[:, None, None]))
-    assert np.array_equal(wb, O.bilinear_interpolation_cws(fr, idx, vx[:, None, None], vy[:, None, None]))
-    assert cases.sha(wb) == str(g[f"cws_{w}_sha"])          # the reference's own output
+    ref_b = O.bilinear_interpolation_cws(fr, idx, vx[:, None, None], vy[:, None, None])
+    assert cases.sha(ref_b) == str(g[f"cws_{w}_sha"])       # the oracle equals the reference's own output
+    assert_cws_windows(wa, O.bilinear_interpolation_cws(fr, idx, -vx[:, None, None], -vy[:, None, None]))
+    assert_cws_windows(wb, ref_b)
     ix, iy = np.rint(vx).astype(np.int64), np.rint(vy).astype(np.int64)
     wa, wb = G.windows(fr, fr, w, o, "DWS", ix, iy)
     assert np.array_equal(wa, O.interpolation_dws(fr, idx, -ix[:, None, None], -iy[:, None, None]).astype(np.float32))
@@ -134,8 +148,8 @@ def test_windows_unaligned_frame_takes_gather_path(G):
         vy = rng.uniform(-9, 9, n).astype(np.float32)
         idx = O.window_index_grid(a.shape, w, o)
         wa, wb = G.windows(a, b, w, o, "CWS", vx, vy)
-        assert np.array_equal(wa, O.bilinear_interpolation_cws(a, idx, -vx[:, None, None], -vy[:, None, None]))
-        assert np.array_equal(wb, O.bilinear_interpolation_cws(b, idx, vx[:, None, None], vy[:, None, None]))
+        assert_cws_windows(wa, O.bilinear_interpolation_cws(a, idx, -vx[:, None, None], -vy[:, None, None]))
+        assert_cws_windows(wb, O.bilinear_interpolation_cws(b, idx, vx[:, None, None], vy[:, None, None]))
 
 
 def test_reference_layout_shift_functions(T, golden):

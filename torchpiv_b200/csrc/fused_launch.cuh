@@ -29,7 +29,13 @@ namespace pivb200 {
 template <int W, int LOADER, int SINK>
 static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const PassParams& p_in,
                       cudaStream_t stream) {
-    const PassParams& p = p_in;
+    PassParams p = p_in;
+    {
+        // lock-step barriers (see piv_fused.cuh); PIVB200_SYNC_MASK overrides for experiments
+        static const int env_mask = [] { const char* e = getenv("PIVB200_SYNC_MASK"); return e ? atoi(e) : -1; }();
+        // measured best on B200: one barrier per job (before the inverse column step) for 64 px, none otherwise
+        p.sync_mask = env_mask >= 0 ? env_mask : (W == 64 ? 16 : 0);
+    }
     using S = Smem<W, LOADER>;
     auto kern = piv_fused_kernel<W, LOADER, SINK>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::CTA_BYTES);

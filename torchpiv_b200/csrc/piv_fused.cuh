@@ -115,7 +115,7 @@ struct Smem {
     static constexpr int BAR_OFF = ((TD_OFF + TD + 7) / 8) * 8;
     static constexpr int TOTAL = BAR_OFF + 8;
     static constexpr int STRIDE = ((TOTAL + 255) / 256) * 256;
-    static constexpr int SMEM_MAX = 232448;           // 227 KB opt-in limit per CTA
+    static constexpr int SMEM_MAX = 232448 - 1024;    // 227 KB opt-in limit per CTA minus the static allocation
     // warps per CTA: bounded by shared memory, by the register file (launch bounds) and by the 512
     // TMEM columns (4 lane quarters x 512 / TCOLS warps)
     static constexpr int WARP_CAP = (W == 64) ? 12 : (W == 32 ? 16 : 24);
@@ -276,14 +276,80 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float2 (&v)[8]) {
         : "memory");
 }
 
-// Parking order of a column spectrum: entry i of the parked array is bin park_bin<W>(i) =
-// 0, W/2, 1, W-1, 2, W-2, ...  Every aligned group of 8 entries is closed under k -> W - k, which is
-// what the lane that owns the packed real columns (0, W/2) needs to separate them chunk by chunk.
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float2 (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x),
+          "=f"(v[3].y), "=f"(v[4].x), "=f"(v[4].y), "=f"(v[5].x), "=f"(v[5].y), "=f"(v[6].x), "=f"(v[6].y),
+          "=f"(v[7].x), "=f"(v[7].y), "=f"(v[8].x), "=f"(v[8].y), "=f"(v[9].x), "=f"(v[9].y), "=f"(v[10].x),
+          "=f"(v[10].y), "=f"(v[11].x), "=f"(v[11].y), "=f"(v[12].x), "=f"(v[12].y), "=f"(v[13].x), "=f"(v[13].y),
+          "=f"(v[14].x), "=f"(v[14].y), "=f"(v[15].x), "=f"(v[15].y)
+        : "r"(taddr)
+        : "memory");
+}
+
+// Parking order of a column spectrum.  After the forward column FFT bin q sits in register slot
+// pos(q) (digit reversed); the inverse transform (same code, same register view) wants element q in
+// slot q.  The product conj(A^) B^ therefore moves its result from slot pos(q) to slot q, which can be
+// done in place as long as whole cycles of the permutation q -> pos(q) are handled together.  The
+// parked spectrum is read back from TMEM in chunks of CH bins; ParkOrder packs whole cycles into
+// chunks (first fit): 8 x 8 and 4 x 4 digit reversals are involutions (cycles of 1 or 2, CH = 8), the
+// 8 x 4 reversal of the 32-point transform has two fixed points and six 5-cycles (CH = 16).
+template <int W>
+struct ParkOrder {
+    static constexpr int CH = (W == 32) ? 16 : 8;
+    static constexpr int NCH = W / CH;
+    int bin[W];
+    constexpr ParkOrder() : bin{} {
+        bool used[W] = {};
+        int fill[NCH] = {};
+        for (int q = 0; q < W; ++q) {
+            if (used[q]) continue;
+            int len = 0;
+            for (int r = q; !used[r]; r = Fft<W>::pos(r)) { used[r] = true; ++len; }
+            int c = 0;
+            while (fill[c] + len > CH) ++c;
+            int r = q;
+            for (int i = 0; i < len; ++i) { bin[c * CH + fill[c] + i] = r; r = Fft<W>::pos(r); }
+            fill[c] += len;
+        }
+    }
+};
 template <int W>
 __host__ __device__ constexpr int park_bin(int i) {
-    if (i == 0) return 0;
-    if (i == 1) return W / 2;
-    return (i & 1) ? W - i / 2 : i / 2;
+    constexpr ParkOrder<W> order{};
+    return order.bin[i];
+}
+
+// Border window (slow path, rare): the reference addresses taps by FLAT index clamped to
+// [0, H*W-1] (PB:172-180, 213-214), i.e. columns that leave the frame wrap into neighbouring rows.
+// The whole warp gathers the tile byte by byte into the layout the TMA would have produced.
+template <int W, int LOADER>
+__device__ __noinline__ void gather_border_tile(const PassParams& p, const TileDesc dsc, unsigned char* tile,
+                                                int frame, int lane) {
+    using T = Tile<W, LOADER>;
+    const unsigned char* f = (frame ? p.fb : p.fa) + dsc.pair * p.pair_stride;
+    const int last_y = p.H - 1, last_x = p.Wf - 1;
+#pragma unroll 2
+    for (int e = lane; e < T::BY * T::USED; e += 32) {
+        const int i = e / T::USED, jj = e - i * T::USED;
+        int yy = dsc.oy + i, xx = dsc.ox + jj;
+        if (xx < 0 || xx > last_x) {
+            // column outside the frame: the flat index wraps into a neighbouring row
+            long long flat = static_cast<long long>(yy) * p.Wf + xx;
+            const long long last = static_cast<long long>(p.H) * p.Wf - 1;
+            flat = flat < 0 ? 0 : (flat > last ? last : flat);
+            const unsigned uf = static_cast<unsigned>(flat);      // H * W < 2^31 (checked on the host)
+            yy = static_cast<int>(uf / static_cast<unsigned>(p.Wf));
+            xx = static_cast<int>(uf - static_cast<unsigned>(yy) * static_cast<unsigned>(p.Wf));
+        } else if (yy < 0) {
+            yy = 0; xx = 0;                 // flat < 0 clamps to the first pixel
+        } else if (yy > last_y) {
+            yy = last_y; xx = last_x;       // flat > H*W-1 clamps to the last pixel
+        }
+        tile[T::off(i, jj >> 4) + (jj & 15)] = f[static_cast<long long>(yy) * p.pitch + xx];
+    }
 }
 
 // ----------------------------------------------------------------------------------------
@@ -297,7 +363,7 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
     using T = Tile<W, LOADER>;
     using S = Smem<W, LOADER>;
     using F = Fft<W>;
-    using FR = FftRev<W>;
+    using PO = ParkOrder<W>;
     constexpr int NW = G::NW, HALF = G::HALF, LOGW = G::LOGW, PX = G::PX, PC = G::PC;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr bool kTmem = (SINK != SK_WIN);
@@ -369,30 +435,7 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                 if (dsc.d >= 0) {
                     tx += T::TX;
                 } else {
-                    // border window: the reference addresses taps by FLAT index clamped to
-                    // [0, H*W-1] (PB:172-180, 213-214), i.e. columns wrap into neighbouring rows.
-                    const unsigned char* f = (frame ? p.fb : p.fa) + dsc.pair * p.pair_stride;
-                    unsigned char* tile = smem + S::REG_OFF + w2 * G::REGION;
-                    const int last_y = p.H - 1, last_x = p.Wf - 1;
-#pragma unroll 4
-                    for (int e = lane; e < T::BY * T::USED; e += 32) {
-                        const int i = e / T::USED, jj = e - i * T::USED;
-                        int yy = dsc.oy + i, xx = dsc.ox + jj;
-                        if (xx < 0 || xx > last_x) {
-                            // column outside the frame: the flat index wraps into a neighbouring row
-                            long long flat = static_cast<long long>(yy) * p.Wf + xx;
-                            const long long last = static_cast<long long>(p.H) * p.Wf - 1;
-                            flat = flat < 0 ? 0 : (flat > last ? last : flat);
-                            const unsigned uf = static_cast<unsigned>(flat);      // H * W < 2^31 (checked on the host)
-                            yy = static_cast<int>(uf / static_cast<unsigned>(p.Wf));
-                            xx = static_cast<int>(uf - static_cast<unsigned>(yy) * static_cast<unsigned>(p.Wf));
-                        } else if (yy < 0) {
-                            yy = 0; xx = 0;                 // flat < 0 clamps to the first pixel
-                        } else if (yy > last_y) {
-                            yy = last_y; xx = last_x;       // flat > H*W-1 clamps to the last pixel
-                        }
-                        tile[T::off(i, jj >> 4) + (jj & 15)] = f[static_cast<long long>(yy) * p.pitch + xx];
-                    }
+                    gather_border_tile<W, LOADER>(p, dsc, smem + S::REG_OFF + w2 * G::REGION, frame, lane);
                 }
             }
             if (tx != 0) {
@@ -424,21 +467,26 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
         }
     };
 
+    // Every warp of the CTA runs the same number of iterations (optional block barriers inside keep the
+    // warps in the same phase so that they share instruction fetches); a warp without work re-does
+    // the last job with its output suppressed.
 #pragma unroll 1
-    for (int job = blockIdx.x * nwarps + warp; job < njobs; job += job_stride) {
+    for (int base = blockIdx.x * nwarps; base < njobs; base += job_stride) {
+        const int job = min(base + warp, njobs - 1);
         const int g = min(job * NW + wi, n_total - 1);       // window of this lane (clamped: the last job may be ragged)
-        const bool g_valid = job * NW + wi < n_total;
+        const bool g_valid = (base + warp < njobs) && (job * NW + wi < n_total);
         make_desc(job);
         stage_issue(0);
 
         float sum_a = 0.f, sum_b = 0.f;        // pixel sums of the window (valid in lanes l == 0)
         float2 x[W];                           // the FFT operand
         // ===================================================================================
-        // Five FFT steps per lane around ONE shared transform body:
-        //   s = 0  Ra    s = 1  Ca (+ park)    s = 2  Rb    s = 3  Cb (+ product, inverse, -> Q)    s = 4  I
+        // Six FFT steps per lane around ONE shared transform body:
+        //   s = 0  Ra    s = 1  Ca (+ park)    s = 2  Rb    s = 3  Cb forward (+ product)    s = 4  Cb inverse (-> Q)    s = 5  I
         // ===================================================================================
 #pragma unroll 1
-        for (int s = 0; s < 5; ++s) {
+        for (int s = 0; s < 6; ++s) {
+            if ((p.sync_mask >> s) & 1) __syncthreads();        // lock step: shared instruction fetch
             // ---------------------------------------------------------------- load
             if (s == 0 || s == 2) {
                 const int frame = s >> 1;
@@ -447,8 +495,8 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                     const TileDesc* desc = reinterpret_cast<const TileDesc*>(smem + S::TD_OFF);
                     const int d = desc[wi * 2 + frame].d;
                     uint32_t w0[W / 4], w1[W / 4];
-                    load_row_words<W, LOADER, W / 4>(region, l, d, w0);
-                    load_row_words<W, LOADER, W / 4>(region, l + HALF, d, w1);
+                    load_row_words<W, LOADER, W / 4>(region, 2 * l, d, w0);
+                    load_row_words<W, LOADER, W / 4>(region, 2 * l + 1, d, w1);
                     static_for<0, W>([&](auto jc) {
                         constexpr int j = decltype(jc)::value;
                         x[j] = make_float2(u8f(w0[j >> 2], j & 3), u8f(w1[j >> 2], j & 3));
@@ -476,53 +524,56 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                     const TileDesc dsc = desc[wi * 2 + frame];
                     const float2* xwq = xw + wi * W;
                     const int* xfq = xf + wi * W;
-                    static_for<0, 2>([&](auto hc) {
-                        constexpr int half = decltype(hc)::value;
-                        const int rt = l + half * HALF;
-                        const AxisTap cy = cws_axis(dsc.r0 + rt, dsc.vy);
-                        const int jy = (cy.lo - (dsc.oy + rt)) & 1;
-                        uint32_t r0w[W / 4 + 1], r1w[W / 4 + 1];
-                        load_row_words<W, LOADER, W / 4 + 1>(region, rt, dsc.d, r0w);
-                        load_row_words<W, LOADER, W / 4 + 1>(region, rt + 1, dsc.d, r1w);
-                        float l0 = u8f(r0w[0], 0), l1 = u8f(r1w[0], 0);
-                        if (!anyflag) {
-                            static_for<0, W>([&](auto jc) {
-                                constexpr int j = decltype(jc)::value;
-                                const float h0 = u8f(r0w[(j + 1) >> 2], (j + 1) & 3);
-                                const float h1 = u8f(r1w[(j + 1) >> 2], (j + 1) & 3);
-                                const float2 wx = xwq[j];
-                                // PB:187-192 evaluation order, no FMA contraction
-                                float acc = __fmul_rn(__fmul_rn(l0, wx.x), cy.w1);
-                                acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(h0, wx.y), cy.w1));
-                                acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(l1, wx.x), cy.w0));
-                                acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(h1, wx.y), cy.w0));
-                                if constexpr (half == 0) x[j].x = acc; else x[j].y = acc;
-                                l0 = h0; l1 = h1;
-                            });
-                        } else {
-                            static_for<0, W>([&](auto jc) {
-                                constexpr int j = decltype(jc)::value;
-                                const float h0 = u8f(r0w[(j + 1) >> 2], (j + 1) & 3);
-                                const float h1 = u8f(r1w[(j + 1) >> 2], (j + 1) & 3);
-                                const float2 wx = xwq[j];
-                                const int fl = xfq[j];
-                                float acc = __fmul_rn(__fmul_rn(l0, wx.x), cy.w1);
-                                acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(h0, wx.y), cy.w1));
-                                acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(l1, wx.x), cy.w0));
-                                acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(h1, wx.y), cy.w0));
-                                // exact-integer coordinate on either axis: tap (floor y, floor x) (PB:170, 193)
-                                const float s0 = (fl & 1) ? h0 : l0, s1 = (fl & 1) ? h1 : l1;
-                                const float q11 = jy ? s1 : s0;
-                                acc = ((fl & 2) || cy.exact) ? q11 : acc;
-                                if constexpr (half == 0) x[j].x = acc; else x[j].y = acc;
-                                l0 = h0; l1 = h1;
-                            });
-                        }
-                    });
+                    // Window rows (2l, 2l+1) need tile rows 2l .. 2l+2.  The reference's four-term sum
+                    // (PB:187-192) is evaluated in its separable form: a horizontal tap h = Q(x) wx1 +
+                    // Q(x+1) wx0 per tile row, shared by the two window rows, then the vertical tap --
+                    // same value up to FP32 rounding (~1e-7 relative; the function-level entry point
+                    // pivb200_bilinear_cws keeps the reference's exact evaluation order).
+                    const int ra = 2 * l;
+                    const AxisTap cyA = cws_axis(dsc.r0 + ra, dsc.vy), cyB = cws_axis(dsc.r0 + ra + 1, dsc.vy);
+                    uint32_t wA[W / 4 + 1], wB[W / 4 + 1], wC[W / 4 + 1];
+                    load_row_words<W, LOADER, W / 4 + 1>(region, ra, dsc.d, wA);
+                    load_row_words<W, LOADER, W / 4 + 1>(region, ra + 1, dsc.d, wB);
+                    load_row_words<W, LOADER, W / 4 + 1>(region, ra + 2, dsc.d, wC);
+                    float cA = u8f(wA[0], 0), cB = u8f(wB[0], 0), cC = u8f(wC[0], 0);
+                    if (!anyflag) {
+                        static_for<0, W>([&](auto jc) {
+                            constexpr int j = decltype(jc)::value;
+                            const float nA = u8f(wA[(j + 1) >> 2], (j + 1) & 3);
+                            const float nB = u8f(wB[(j + 1) >> 2], (j + 1) & 3);
+                            const float nC = u8f(wC[(j + 1) >> 2], (j + 1) & 3);
+                            const float2 wx = xwq[j];
+                            const float hA = fmaf(cA, wx.x, nA * wx.y);
+                            const float hB = fmaf(cB, wx.x, nB * wx.y);
+                            const float hC = fmaf(cC, wx.x, nC * wx.y);
+                            x[j] = make_float2(fmaf(hA, cyA.w1, hB * cyA.w0), fmaf(hB, cyB.w1, hC * cyB.w0));
+                            cA = nA; cB = nB; cC = nC;
+                        });
+                    } else {
+                        // some coordinate of the job is an exact integer: there the reference's weights all
+                        // vanish and the value is patched to the tap at (floor y, floor x) (PB:170, 193)
+                        const bool jyA = (cyA.lo - (dsc.oy + ra)) & 1, jyB = (cyB.lo - (dsc.oy + ra + 1)) & 1;
+                        static_for<0, W>([&](auto jc) {
+                            constexpr int j = decltype(jc)::value;
+                            const float nA = u8f(wA[(j + 1) >> 2], (j + 1) & 3);
+                            const float nB = u8f(wB[(j + 1) >> 2], (j + 1) & 3);
+                            const float nC = u8f(wC[(j + 1) >> 2], (j + 1) & 3);
+                            const float2 wx = xwq[j];
+                            const int fl = xfq[j];
+                            const float hA = fmaf(cA, wx.x, nA * wx.y);
+                            const float hB = fmaf(cB, wx.x, nB * wx.y);
+                            const float hC = fmaf(cC, wx.x, nC * wx.y);
+                            const float qA = (fl & 1) ? nA : cA, qB = (fl & 1) ? nB : cB, qC = (fl & 1) ? nC : cC;
+                            const float vA = ((fl & 2) || cyA.exact) ? (jyA ? qB : qA) : fmaf(hA, cyA.w1, hB * cyA.w0);
+                            const float vB = ((fl & 2) || cyB.exact) ? (jyB ? qC : qB) : fmaf(hB, cyB.w1, hC * cyB.w0);
+                            x[j] = make_float2(vA, vB);
+                            cA = nA; cB = nB; cC = nC;
+                        });
+                    }
                 } else if constexpr (LOADER == LD_EXPL_F32) {
                     const float* base = static_cast<const float*>(frame ? p.wb : p.wa) + static_cast<long long>(g) * W * W;
-                    const float4* r0 = reinterpret_cast<const float4*>(base + l * W);
-                    const float4* r1 = reinterpret_cast<const float4*>(base + (l + HALF) * W);
+                    const float4* r0 = reinterpret_cast<const float4*>(base + 2 * l * W);
+                    const float4* r1 = reinterpret_cast<const float4*>(base + (2 * l + 1) * W);
                     static_for<0, W / 4>([&](auto cc) {
                         constexpr int c = decltype(cc)::value;
                         const float4 va = __ldg(r0 + c), vb = __ldg(r1 + c);
@@ -533,8 +584,8 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                     });
                 } else {
                     const unsigned char* base = static_cast<const unsigned char*>(frame ? p.wb : p.wa) + static_cast<long long>(g) * W * W;
-                    const uint4* r0 = reinterpret_cast<const uint4*>(base + l * W);
-                    const uint4* r1 = reinterpret_cast<const uint4*>(base + (l + HALF) * W);
+                    const uint4* r0 = reinterpret_cast<const uint4*>(base + 2 * l * W);
+                    const uint4* r1 = reinterpret_cast<const uint4*>(base + (2 * l + 1) * W);
                     static_for<0, W / 16>([&](auto cc) {
                         constexpr int c = decltype(cc)::value;
                         const uint4 qa = __ldg(r0 + c), qb = __ldg(r1 + c);
@@ -551,8 +602,8 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                 if constexpr (SINK == SK_WIN) {
                     if (g_valid) {
                         float* dst = (frame ? p.win_b_out : p.win_a_out) + static_cast<long long>(g) * W * W;
-                        float4* o0 = reinterpret_cast<float4*>(dst + l * W);
-                        float4* o1 = reinterpret_cast<float4*>(dst + (l + HALF) * W);
+                        float4* o0 = reinterpret_cast<float4*>(dst + 2 * l * W);
+                        float4* o1 = reinterpret_cast<float4*>(dst + (2 * l + 1) * W);
                         static_for<0, W / 4>([&](auto cc) {
                             constexpr int c = decltype(cc)::value;
                             o0[c] = make_float4(x[4 * c].x, x[4 * c + 1].x, x[4 * c + 2].x, x[4 * c + 3].x);
@@ -564,10 +615,14 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                     continue;
                 }
             } else if (s == 1 || s == 3) {
-                static_for<0, W>([&](auto tc) { constexpr int t = decltype(tc)::value; x[t] = Xw[t * PX + l]; });
+                // window row t lives in buffer row (t >> 1) + (t & 1) * H (the row lanes store there, conflict free)
+                static_for<0, W>([&](auto tc) {
+                    constexpr int t = decltype(tc)::value;
+                    x[t] = Xw[((t >> 1) + (t & 1) * HALF) * PX + l];
+                });
                 __syncwarp();                   // X fully read: the buffer is dead
                 if (s == 1) stage_issue(1);     // frame b tiles arrive while column a is transformed
-            } else {
+            } else if (s == 5) {
                 // two Hermitian rows l, l + W/2 of Q packed into one complex inverse FFT
                 const float2 a0 = Xw[l * PX], b0 = Xw[(l + HALF) * PX];
                 x[0] = make_float2(b0.x, a0.x);
@@ -614,65 +669,71 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                 }
             } else if (s == 3) {
                 if constexpr (kTmem) {
-                    static_for<0, W / 8>([&](auto cc) {
+                    // The lane that owns the packed real columns (0, W/2), l == 0, needs bins q and W - q of
+                    // both spectra at once to separate them.  It drops its two spectra into the (dead)
+                    // window buffer and the H lanes of the window do the H + 1 small pair jobs in parallel.
+                    float2* const sB = Xw;              // [W] b spectrum of column 0, natural order
+                    float2* const sA = Xw + W;          // [W] parked a spectrum
+                    float2* const sV = Xw + 2 * W;      // [W] inverse-transform input of column 0, stored (im, re)
+                    if (l == 0) {
+                        static_for<0, W>([&](auto qc) { constexpr int q = decltype(qc)::value; sB[q] = x[F::pos(q)]; });
+                    }
+                    static_for<0, PO::NCH>([&](auto cc) {
                         constexpr int c = decltype(cc)::value;
-                        float2 A[8];
-                        tmem_ld8(tpark + 16 * c, A);
+                        constexpr int CH = PO::CH;
+                        float2 A[CH];
+                        if constexpr (CH == 8) tmem_ld8(tpark + 2 * CH * c, A);
+                        else tmem_ld16(tpark + 2 * CH * c, A);
                         tmem_wait_ld();
-                        if (l != 0) {
-                            // P = conj(A^) B^, stored (im, re) for the inverse transform
-                            static_for<0, 8>([&](auto ic) {
-                                constexpr int i = decltype(ic)::value;
-                                constexpr int sl = F::pos(park_bin<W>(8 * c + i));
-                                const float2 B = x[sl];
-                                x[sl] = make_float2(fmaf(A[i].x, B.y, -A[i].y * B.x), fmaf(A[i].x, B.x, A[i].y * B.y));
-                            });
-                        } else {
-                            // packed real columns 0 and W/2: C = c0^ + i cH^.  Separate, multiply, re-pack.
-                            static_for<0, 4>([&](auto mc) {
-                                constexpr int m = decltype(mc)::value;
-                                constexpr int i0 = 8 * c + 2 * m;
-                                if constexpr (i0 == 0) {
-                                    // bins 0 and W/2 are their own partners: everything is real
-                                    static_for<0, 2>([&](auto ec) {
-                                        constexpr int e = decltype(ec)::value;
-                                        constexpr int sl = F::pos(park_bin<W>(e));
-                                        const float2 B = x[sl];
-                                        float p0 = A[e].x * B.x;
-                                        const float ph = A[e].y * B.y;
-                                        if constexpr (e == 0) {
-                                            sum_a = 0.5f * A[e].x;
-                                            sum_b = 0.5f * B.x;
-                                            // drop the DC bin (mean product): a constant that `- amin` removes anyway
-                                            if constexpr (SINK == SK_DISP) p0 = 0.f;
-                                        }
-                                        x[sl] = make_float2(ph, p0);
-                                    });
-                                } else {
-                                    constexpr int sq = F::pos(park_bin<W>(i0)), sn = F::pos(park_bin<W>(i0 + 1));
-                                    const float2 Aq = A[2 * m], An = A[2 * m + 1], Bq = x[sq], Bn = x[sn];
-                                    const float2 a0 = make_float2(Aq.x + An.x, Aq.y - An.y);      // 2 c0^[q]
-                                    const float2 ah = make_float2(Aq.y + An.y, An.x - Aq.x);      // 2 cH^[q]
-                                    const float2 b0 = make_float2(0.25f * (Bq.x + Bn.x), 0.25f * (Bq.y - Bn.y));
-                                    const float2 bh = make_float2(0.25f * (Bq.y + Bn.y), 0.25f * (Bn.x - Bq.x));
-                                    const float2 P0 = make_float2(fmaf(a0.x, b0.x, a0.y * b0.y), fmaf(a0.x, b0.y, -a0.y * b0.x));
-                                    const float2 Ph = make_float2(fmaf(ah.x, bh.x, ah.y * bh.y), fmaf(ah.x, bh.y, -ah.y * bh.x));
-                                    // V[q] = P0 + i Ph, V[W-q] = conj(P0) + i conj(Ph); stored (im, re)
-                                    x[sq] = make_float2(P0.y + Ph.x, P0.x - Ph.y);
-                                    x[sn] = make_float2(Ph.x - P0.y, P0.x + Ph.y);
-                                }
-                            });
+                        if (l == 0) {
+                            static_for<0, CH>([&](auto ic) { constexpr int i = decltype(ic)::value; sA[park_bin<W>(CH * c + i)] = A[i]; });
                         }
-                        __syncwarp();
-                    });
-                    FR::run(x);
-                    static_for<0, W>([&](auto tc) {
-                        constexpr int t = decltype(tc)::value;
-                        const float2 o = x[FR::slot(t)];
-                        Xw[t * PX + l] = make_float2(o.y, o.x);
+                        // P[q] = conj(A^[q]) B^[q]: read from slot pos(q), stored (im, re) into slot q for the
+                        // inverse transform (the chunk is closed under q -> pos(q), so this is in place)
+                        float2 P[CH];
+                        static_for<0, CH>([&](auto ic) {
+                            constexpr int i = decltype(ic)::value;
+                            const float2 B = x[F::pos(park_bin<W>(CH * c + i))];
+                            P[i] = make_float2(fmaf(A[i].x, B.y, -A[i].y * B.x), fmaf(A[i].x, B.x, A[i].y * B.y));
+                        });
+                        static_for<0, CH>([&](auto ic) { constexpr int i = decltype(ic)::value; x[park_bin<W>(CH * c + i)] = P[i]; });
                     });
                     __syncwarp();
+                    if (l == 0) {
+                        // bins 0 and W/2 are their own partners: everything is real
+                        const float2 A0 = sA[0], B0 = sB[0], Ah = sA[HALF], Bh = sB[HALF];
+                        sum_a = 0.5f * A0.x;
+                        sum_b = 0.5f * B0.x;
+                        // drop the DC bin (mean product): a constant that `- amin` removes anyway
+                        const float p00 = (SINK == SK_DISP) ? 0.f : A0.x * B0.x;
+                        sV[0] = make_float2(A0.y * B0.y, p00);
+                        sV[HALF] = make_float2(Ah.y * Bh.y, Ah.x * Bh.x);
+                    } else {
+                        // C = c0^ + i cH^ (two real columns): separate, multiply, re-pack
+                        const float2 Aq = sA[l], An = sA[W - l], Bq = sB[l], Bn = sB[W - l];
+                        const float2 a0 = make_float2(Aq.x + An.x, Aq.y - An.y);      // 2 c0^[q]
+                        const float2 ah = make_float2(Aq.y + An.y, An.x - Aq.x);      // 2 cH^[q]
+                        const float2 b0 = make_float2(0.25f * (Bq.x + Bn.x), 0.25f * (Bq.y - Bn.y));
+                        const float2 bh = make_float2(0.25f * (Bq.y + Bn.y), 0.25f * (Bn.x - Bq.x));
+                        const float2 P0 = make_float2(fmaf(a0.x, b0.x, a0.y * b0.y), fmaf(a0.x, b0.y, -a0.y * b0.x));
+                        const float2 Ph = make_float2(fmaf(ah.x, bh.x, ah.y * bh.y), fmaf(ah.x, bh.y, -ah.y * bh.x));
+                        // V[q] = P0 + i Ph, V[W-q] = conj(P0) + i conj(Ph); stored (im, re)
+                        sV[l] = make_float2(P0.y + Ph.x, P0.x - Ph.y);
+                        sV[W - l] = make_float2(Ph.x - P0.y, P0.x + Ph.y);
+                    }
+                    __syncwarp();
+                    if (l == 0) {
+                        static_for<0, W>([&](auto qc) { constexpr int q = decltype(qc)::value; x[q] = sV[q]; });
+                    }
+                    __syncwarp();                       // scratch fully read before Q overwrites the buffer
                 }
+            } else if (s == 4) {
+                static_for<0, W>([&](auto tc) {
+                    constexpr int t = decltype(tc)::value;
+                    const float2 o = x[F::pos(t)];
+                    Xw[t * PX + l] = make_float2(o.y, o.x);
+                });
+                __syncwarp();
             }
         }
         if constexpr (SINK == SK_WIN) continue;
@@ -696,7 +757,7 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
 #pragma unroll 1
             for (int w2 = 0; w2 < NW; ++w2) {
                 const int g2 = job * NW + w2;
-                if (g2 >= n_total) break;
+                if (base + warp >= njobs || g2 >= n_total) break;
                 const float* mw = reinterpret_cast<const float*>(smem + S::REG_OFF + w2 * G::REGION);
                 float* out = p.corr_out + static_cast<long long>(g2) * W * W;
                 for (int e = lane; e < W * W; e += 32)
@@ -742,7 +803,12 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
             const double cr = (static_cast<double>(at(ir)) - dmin) + eps;
             const double ct = (static_cast<double>(at(it_)) - dmin) + eps;
             const double cb = (static_cast<double>(at(ib)) - dmin) + eps;
-            const double lm = log(cm), ll = log(cl), lr = log(cr), lt = log(ct), lb = log(cb);
+            // the five logarithms are evaluated by five lanes of the window (one log() body, 1/5 of the FP64 work)
+            const double lsel = (l == 0) ? cm : (l == 1) ? cl : (l == 2) ? cr : (l == 3) ? ct : cb;
+            const double lg = log(lsel);
+            const int l0 = wi * HALF;
+            const double lm = __shfl_sync(FULL, lg, l0), ll = __shfl_sync(FULL, lg, l0 + 1), lr = __shfl_sync(FULL, lg, l0 + 2),
+                         lt = __shfl_sync(FULL, lg, l0 + 3), lb = __shfl_sync(FULL, lg, l0 + 4);
             double du = static_cast<double>(C) + (lr - ll) / (2.0 * (ll + lr) - 4.0 * lm) - static_cast<double>(HALF);
             double dv = static_cast<double>(R) + (lb - lt) / (2.0 * (lb + lt) - 4.0 * lm) - static_cast<double>(HALF);
             // torch.nan_to_num (PB:418-419)

@@ -41,6 +41,7 @@ struct PassParams {
     unsigned char* mask;             // 1 = invalid (peak ratio test), may be null when !validate
     float* ratio;                    // optional peak / second-peak ratio
     int use_tma;
+    int sync_mask;                   // bit s: block barrier before FFT step s (0..4)
     // explicit loaders / debug sinks
     const void* wa;
     const void* wb;
