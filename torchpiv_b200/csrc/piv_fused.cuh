@@ -49,7 +49,12 @@ struct Geo {
     static constexpr int PC = W + 1;                  // pitch of map rows (float)
     static constexpr int XB = W * PX * 8;
     static constexpr int MAPB = W * PC * 4;
-    static constexpr int REGION = (((XB > MAPB ? XB : MAPB) + 255) / 256) * 256;   // one window's buffer
+    // Bank staggering: the windows of one warp keep their X / Q / map data at different offsets inside
+    // their buffers (0, 64, 32, 96 bytes), so that lanes of different windows that execute the same
+    // shared-memory instruction hit different banks.  The TMA tile always starts at the buffer base.
+    static constexpr int STAGGER = (NW > 1) ? 96 : 0;
+    __host__ __device__ static constexpr int doff(int wi) { return ((wi & 1) * 64) + ((wi >> 1) * 32); }
+    static constexpr int REGION = (((XB > MAPB ? XB : MAPB) + STAGGER + 255) / 256) * 256;   // one window's buffer
     static constexpr float K = 4.0f * W * W;          // map = K * sum_x a(x) b(x+s)
     static constexpr int TCOLS = 2 * W;               // TMEM columns (32-bit) one warp parks
 };
@@ -165,6 +170,8 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
+// byte b of `word` as a float.  (A PRMT + FADD(-2^23) pair that avoids the quarter-rate XU pipe was
+// measured: -2 % for the 64 px pass, +3 % for the 32 px passes -- not kept.)
 __device__ __forceinline__ float u8f(uint32_t word, int b) {
     return static_cast<float>((word >> (8 * b)) & 0xffu);
 }
@@ -367,6 +374,9 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
     constexpr int NW = G::NW, HALF = G::HALF, LOGW = G::LOGW, PX = G::PX, PC = G::PC;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr bool kTmem = (SINK != SK_WIN);
+    // rows of the window a lane transforms together: (2l, 2l+1) for CWS (they share the middle tile row's
+    // horizontal taps), (l, l+H) otherwise (conflict-free tile reads)
+    constexpr bool kAdjRows = (LOADER == LD_FRAME_CWS);
 
     extern __shared__ __align__(1024) unsigned char smem_cta[];
     __shared__ uint32_t tmem_base_sh;
@@ -397,7 +407,7 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
     const int wi = lane / HALF;            // window of this lane inside the job
     const int l = lane % HALF;             // rows (l, l + H) in phases R and I, column l in phase C
     unsigned char* const region = smem + S::REG_OFF + wi * G::REGION;
-    float2* const Xw = reinterpret_cast<float2*>(region);
+    float2* const Xw = reinterpret_cast<float2*>(region + G::doff(wi));      // X / Q / map of this lane's window
 
     // ---- descriptors of the (window, frame) tiles of one job ------------------------------
     auto make_desc = [&](int job) {
@@ -495,8 +505,8 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                     const TileDesc* desc = reinterpret_cast<const TileDesc*>(smem + S::TD_OFF);
                     const int d = desc[wi * 2 + frame].d;
                     uint32_t w0[W / 4], w1[W / 4];
-                    load_row_words<W, LOADER, W / 4>(region, 2 * l, d, w0);
-                    load_row_words<W, LOADER, W / 4>(region, 2 * l + 1, d, w1);
+                    load_row_words<W, LOADER, W / 4>(region, l, d, w0);
+                    load_row_words<W, LOADER, W / 4>(region, l + HALF, d, w1);
                     static_for<0, W>([&](auto jc) {
                         constexpr int j = decltype(jc)::value;
                         x[j] = make_float2(u8f(w0[j >> 2], j & 3), u8f(w1[j >> 2], j & 3));
@@ -572,8 +582,8 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                     }
                 } else if constexpr (LOADER == LD_EXPL_F32) {
                     const float* base = static_cast<const float*>(frame ? p.wb : p.wa) + static_cast<long long>(g) * W * W;
-                    const float4* r0 = reinterpret_cast<const float4*>(base + 2 * l * W);
-                    const float4* r1 = reinterpret_cast<const float4*>(base + (2 * l + 1) * W);
+                    const float4* r0 = reinterpret_cast<const float4*>(base + l * W);
+                    const float4* r1 = reinterpret_cast<const float4*>(base + (l + HALF) * W);
                     static_for<0, W / 4>([&](auto cc) {
                         constexpr int c = decltype(cc)::value;
                         const float4 va = __ldg(r0 + c), vb = __ldg(r1 + c);
@@ -584,8 +594,8 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                     });
                 } else {
                     const unsigned char* base = static_cast<const unsigned char*>(frame ? p.wb : p.wa) + static_cast<long long>(g) * W * W;
-                    const uint4* r0 = reinterpret_cast<const uint4*>(base + 2 * l * W);
-                    const uint4* r1 = reinterpret_cast<const uint4*>(base + (2 * l + 1) * W);
+                    const uint4* r0 = reinterpret_cast<const uint4*>(base + l * W);
+                    const uint4* r1 = reinterpret_cast<const uint4*>(base + (l + HALF) * W);
                     static_for<0, W / 16>([&](auto cc) {
                         constexpr int c = decltype(cc)::value;
                         const uint4 qa = __ldg(r0 + c), qb = __ldg(r1 + c);
@@ -602,8 +612,8 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                 if constexpr (SINK == SK_WIN) {
                     if (g_valid) {
                         float* dst = (frame ? p.win_b_out : p.win_a_out) + static_cast<long long>(g) * W * W;
-                        float4* o0 = reinterpret_cast<float4*>(dst + 2 * l * W);
-                        float4* o1 = reinterpret_cast<float4*>(dst + (2 * l + 1) * W);
+                        float4* o0 = reinterpret_cast<float4*>(dst + (kAdjRows ? 2 * l : l) * W);
+                        float4* o1 = reinterpret_cast<float4*>(dst + (kAdjRows ? 2 * l + 1 : l + HALF) * W);
                         static_for<0, W / 4>([&](auto cc) {
                             constexpr int c = decltype(cc)::value;
                             o0[c] = make_float4(x[4 * c].x, x[4 * c + 1].x, x[4 * c + 2].x, x[4 * c + 3].x);
@@ -615,10 +625,11 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                     continue;
                 }
             } else if (s == 1 || s == 3) {
-                // window row t lives in buffer row (t >> 1) + (t & 1) * H (the row lanes store there, conflict free)
+                // lane l' stored the spectra of its two window rows in buffer rows l' and l' + H
                 static_for<0, W>([&](auto tc) {
                     constexpr int t = decltype(tc)::value;
-                    x[t] = Xw[((t >> 1) + (t & 1) * HALF) * PX + l];
+                    constexpr int brow = kAdjRows ? (t >> 1) + (t & 1) * HALF : t;
+                    x[t] = Xw[brow * PX + l];
                 });
                 __syncwarp();                   // X fully read: the buffer is dead
                 if (s == 1) stage_issue(1);     // frame b tiles arrive while column a is transformed
@@ -739,7 +750,7 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
         if constexpr (SINK == SK_WIN) continue;
 
         // raw row l -> shifted row l + W/2 (values x[].y); raw row l + W/2 -> shifted row l (x[].x)
-        float* mapw = reinterpret_cast<float*>(region);
+        float* mapw = reinterpret_cast<float*>(Xw);
         float mx_hi = -FLT_MAX, mx_lo = -FLT_MAX, mn = FLT_MAX;     // hi: shifted row l + HALF
         static_for<0, W>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
@@ -758,7 +769,7 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
             for (int w2 = 0; w2 < NW; ++w2) {
                 const int g2 = job * NW + w2;
                 if (base + warp >= njobs || g2 >= n_total) break;
-                const float* mw = reinterpret_cast<const float*>(smem + S::REG_OFF + w2 * G::REGION);
+                const float* mw = reinterpret_cast<const float*>(smem + S::REG_OFF + w2 * G::REGION + G::doff(w2));
                 float* out = p.corr_out + static_cast<long long>(g2) * W * W;
                 for (int e = lane; e < W * W; e += 32)
                     out[e] = mw[(e >> LOGW) * PC + (e & (W - 1))] * (1.0f / G::K);
