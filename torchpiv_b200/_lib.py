@@ -9,7 +9,8 @@ import os
 from ctypes import c_char_p, c_double, c_int, c_longlong, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpivb200.so")
+# PIVB200_LIB selects another build of the same library (A/B experiments); default: the in-tree build
+LIB_PATH = os.environ.get("PIVB200_LIB") or os.path.join(_HERE, "libpivb200.so")
 
 E_WINDOW, E_OVERLAP, E_FRAME, E_ARG, E_DRIVER, E_SIZE = -1, -2, -3, -4, -5, -6
 MODE_DWS, MODE_CWS = 0, 1

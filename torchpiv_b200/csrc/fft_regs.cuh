@@ -63,6 +63,34 @@ __host__ __device__ constexpr double ct_sin2pi(int k, int n) { return ct_cos2pi(
 
 constexpr float kSqrtHalf = 0.70710678118654752440f;
 
+// Complex add / subtract as ONE packed FP32 instruction (sm_100a FADD2 / FFMA2: two lanes of a 64-bit
+// register pair per issue slot -- same FLOP rate as the scalar forms, half the issue slots; the fused
+// kernels are issue bound).  Host builds (unit tests of the index logic) use plain arithmetic.
+__host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+    return __fadd2_rn(a, b);
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+__host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+    return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a);
+#else
+    return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
+// a * s (real s)
+__host__ __device__ __forceinline__ float2 cscale(float2 a, float s) {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+    return __fmul2_rn(a, make_float2(s, s));
+#else
+    return make_float2(a.x * s, a.y * s);
+#endif
+}
+// -i (a - b), computed directly as the rotated pair (two scalar subtractions)
+__host__ __device__ __forceinline__ float2 csub_mi(float2 a, float2 b) { return make_float2(a.y - b.y, b.x - a.x); }
+
 // a * e^{-2 pi i K / N}
 template <int K, int N>
 __host__ __device__ __forceinline__ float2 mul_tw(float2 a) {
@@ -76,22 +104,19 @@ __host__ __device__ __forceinline__ float2 mul_tw(float2 a) {
     } else if constexpr (4 * k == 3 * N) {        // +i
         return make_float2(-a.y, a.x);
     } else if constexpr (8 * k == N) {            // (1 - i)/sqrt2
-        return make_float2(kSqrtHalf * (a.x + a.y), kSqrtHalf * (a.y - a.x));
+        return cscale(make_float2(a.x + a.y, a.y - a.x), kSqrtHalf);
     } else if constexpr (8 * k == 3 * N) {        // (-1 - i)/sqrt2
-        return make_float2(kSqrtHalf * (a.y - a.x), -kSqrtHalf * (a.x + a.y));
+        return cscale(make_float2(a.y - a.x, -a.x - a.y), kSqrtHalf);
     } else if constexpr (8 * k == 5 * N) {        // (-1 + i)/sqrt2
-        return make_float2(-kSqrtHalf * (a.x + a.y), kSqrtHalf * (a.x - a.y));
+        return cscale(make_float2(-a.x - a.y, a.x - a.y), kSqrtHalf);
     } else if constexpr (8 * k == 7 * N) {        // (1 + i)/sqrt2
-        return make_float2(kSqrtHalf * (a.x - a.y), kSqrtHalf * (a.x + a.y));
+        return cscale(make_float2(a.x - a.y, a.x + a.y), kSqrtHalf);
     } else {
         constexpr float c = float(ct_cos2pi(k, N));
         constexpr float s = float(-ct_sin2pi(k, N));
         return make_float2(fmaf(a.x, c, -a.y * s), fmaf(a.x, s, a.y * c));
     }
 }
-
-__host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
 // ----------------------------------------------------------------------------------------
 // small DFTs, natural order in and out, forward sign
@@ -102,11 +127,12 @@ __host__ __device__ __forceinline__ void dft2(float2& a0, float2& a1) {
     a1 = t;
 }
 __host__ __device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
-    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = csub(a1, a3);
+    const float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3);
+    const float2 t3 = csub_mi(a1, a3);              // -i (a1 - a3)
     a0 = cadd(t0, t2);
     a2 = csub(t0, t2);
-    a1 = make_float2(t1.x + t3.y, t1.y - t3.x);     // t1 - i t3
-    a3 = make_float2(t1.x - t3.y, t1.y + t3.x);     // t1 + i t3
+    a1 = cadd(t1, t3);                              // t1 - i (a1 - a3)
+    a3 = csub(t1, t3);                              // t1 + i (a1 - a3)
 }
 template <int R>
 __host__ __device__ __forceinline__ void dft_small(float2 (&a)[R]) {
@@ -117,9 +143,12 @@ __host__ __device__ __forceinline__ void dft_small(float2 (&a)[R]) {
     } else {
         static_assert(R == 8, "radix");
         float2 b0 = cadd(a[0], a[4]), d0 = csub(a[0], a[4]);
-        float2 b1 = cadd(a[1], a[5]), d1 = mul_tw<1, 8>(csub(a[1], a[5]));
-        float2 b2 = cadd(a[2], a[6]), d2 = mul_tw<2, 8>(csub(a[2], a[6]));
-        float2 b3 = cadd(a[3], a[7]), d3 = mul_tw<3, 8>(csub(a[3], a[7]));
+        float2 b1 = cadd(a[1], a[5]);
+        float2 b2 = cadd(a[2], a[6]), d2 = csub_mi(a[2], a[6]);                 // * e^{-2 pi i 2/8} = -i
+        float2 b3 = cadd(a[3], a[7]);
+        const float2 u = csub(a[1], a[5]), v = csub(a[3], a[7]);
+        float2 d1 = cscale(make_float2(u.x + u.y, u.y - u.x), kSqrtHalf);        // * (1 - i)/sqrt2
+        float2 d3 = cscale(make_float2(v.y - v.x, -v.x - v.y), kSqrtHalf);       // * (-1 - i)/sqrt2
         dft4(b0, b1, b2, b3);       // X0 X2 X4 X6
         dft4(d0, d1, d2, d3);       // X1 X3 X5 X7
         a[0] = b0; a[2] = b1; a[4] = b2; a[6] = b3;

@@ -33,8 +33,14 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const PassPa
     {
         // lock-step barriers (see piv_fused.cuh); PIVB200_SYNC_MASK overrides for experiments
         static const int env_mask = [] { const char* e = getenv("PIVB200_SYNC_MASK"); return e ? atoi(e) : -1; }();
-        // measured best on B200: one barrier per job (before the inverse column step) for 64 px, none otherwise
-        p.sync_mask = env_mask >= 0 ? env_mask : (W == 64 ? 16 : 0);
+        // measured best on B200: one barrier per job (before the inverse column step) inside groups of four
+        // warps (one per scheduler): a group shares its instruction fetches, different groups overlap their
+        // FP-bound and shared-memory-bound phases
+        p.sync_mask = env_mask >= 0 ? env_mask : 16;
+        static const int env_group = [] { const char* e = getenv("PIVB200_SYNC_GROUP"); return e ? atoi(e) : 1; }();
+        static const int env_skew = [] { const char* e = getenv("PIVB200_SKEW_NS"); return e ? atoi(e) : 0; }();
+        p.sync_group = env_group;
+        p.skew_ns = env_skew;
     }
     using S = Smem<W, LOADER>;
     auto kern = piv_fused_kernel<W, LOADER, SINK>;
@@ -47,7 +53,8 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const PassPa
     const long long njobs = (p.n_total + Geo<W>::NW - 1) / Geo<W>::NW;
     // PIVB200_NWARPS caps the warps per CTA (occupancy experiments)
     static const int env_warps = [] { const char* e = getenv("PIVB200_NWARPS"); return e ? atoi(e) : 0; }();
-    const int nwarps = (env_warps > 0 && env_warps < S::NWARPS) ? env_warps : S::NWARPS;
+    int nwarps = (env_warps > 0 && env_warps < S::NWARPS) ? env_warps : S::NWARPS;
+    if (p.sync_group) nwarps &= ~3;
     long long grid = (njobs + nwarps - 1) / nwarps;
     if (grid > sms) grid = sms;
     kern<<<static_cast<unsigned>(grid), nwarps * 32, S::CTA_BYTES, stream>>>(ta, tb, p);

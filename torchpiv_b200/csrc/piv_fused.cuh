@@ -123,7 +123,16 @@ struct Smem {
     static constexpr int SMEM_MAX = 232448 - 1024;    // 227 KB opt-in limit per CTA minus the static allocation
     // warps per CTA: bounded by shared memory, by the register file (launch bounds) and by the 512
     // TMEM columns (4 lane quarters x 512 / TCOLS warps)
-    static constexpr int WARP_CAP = (W == 64) ? 12 : (W == 32 ? 16 : 24);
+#ifndef PIVB200_W64_WARPS
+#define PIVB200_W64_WARPS 12
+#endif
+#ifndef PIVB200_W32_WARPS
+#define PIVB200_W32_WARPS 16
+#endif
+#ifndef PIVB200_W16_WARPS
+#define PIVB200_W16_WARPS 24
+#endif
+    static constexpr int WARP_CAP = (W == 64) ? PIVB200_W64_WARPS : (W == 32 ? PIVB200_W32_WARPS : PIVB200_W16_WARPS);
     static constexpr int TMEM_CAP = 4 * (512 / G::TCOLS);
     static constexpr int BY_SMEM = SMEM_MAX / STRIDE;
     static constexpr int NWARPS0 = BY_SMEM < WARP_CAP ? BY_SMEM : WARP_CAP;
@@ -480,6 +489,7 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
     // Every warp of the CTA runs the same number of iterations (optional block barriers inside keep the
     // warps in the same phase so that they share instruction fetches); a warp without work re-does
     // the last job with its output suppressed.
+    if (p.sync_group && p.skew_ns > 0) __nanosleep(static_cast<unsigned>(p.skew_ns) * static_cast<unsigned>(warp >> 2));
 #pragma unroll 1
     for (int base = blockIdx.x * nwarps; base < njobs; base += job_stride) {
         const int job = min(base + warp, njobs - 1);
@@ -496,7 +506,12 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
         // ===================================================================================
 #pragma unroll 1
         for (int s = 0; s < 6; ++s) {
-            if ((p.sync_mask >> s) & 1) __syncthreads();        // lock step: shared instruction fetch
+            if ((p.sync_mask >> s) & 1) {
+                // lock step (shared instruction fetch): the whole CTA, or groups of four warps (one per
+                // scheduler) so that different groups sit in different phases (FP vs shared-memory bound)
+                if (p.sync_group) asm volatile("bar.sync %0, 128;" ::"r"(1 + (warp >> 2)) : "memory");
+                else __syncthreads();
+            }
             // ---------------------------------------------------------------- load
             if (s == 0 || s == 2) {
                 const int frame = s >> 1;
