@@ -40,23 +40,35 @@ def _neighbour_ring(invalid: np.ndarray) -> np.ndarray:
     return grown & ~invalid
 
 
-def fill_holes(field: np.ndarray):
+def fill_holes(field: np.ndarray, *more: np.ndarray):
     """Fill NaNs by piecewise-linear (Delaunay) interpolation over the ring of valid neighbours.
     Returns None -- the caller then skips the pair, as the reference does -- when the ring is
     empty (no invalid vector at all), when the triangulation fails, or when the ring covers a
-    quarter of the field or more ("too many false vectors")."""
+    quarter of the field or more ("too many false vectors").
+
+    ``more``: further fields with the SAME NaN pattern (u and v of one pair).  They share one
+    triangulation (the reference triangulates the identical point set twice, PB:885-890; Qhull is
+    deterministic, so the values are the same and the dominant cost is halved); the return value
+    is then a tuple of the filled fields."""
+    fields = (field,) + more
     invalid = np.isnan(field)
+    for other in more:
+        if not np.array_equal(np.isnan(other), invalid):      # different holes: fall back to one by one
+            out = tuple(fill_holes(f) for f in fields)
+            return None if any(o is None for o in out) else out
     ring = _neighbour_ring(invalid)
     support = np.argwhere(ring)
     if not support.size < ring.size / 2:
         print("Warning! to many false vectors")
         return None
     try:
-        interp = LinearNDInterpolator(support, field[ring])
-        field[invalid] = interp(np.argwhere(invalid))
+        values = np.stack([f[ring] for f in fields], axis=1)
+        filled = LinearNDInterpolator(support, values)(np.argwhere(invalid))
+        for k, f in enumerate(fields):
+            f[invalid] = filled[:, k]
     except Exception:
         return None
-    return field
+    return fields if more else field
 
 
 def finalize_field(u, v, x, y, invalid, scale: float = 1.0, dt: float = 1.0):
@@ -64,10 +76,10 @@ def finalize_field(u, v, x, y, invalid, scale: float = 1.0, dt: float = 1.0):
     if invalid is not None:
         u[invalid] = np.nan
         v[invalid] = np.nan
-        u = fill_holes(fill_borders(u))
-        v = fill_holes(fill_borders(v))
-        if u is None or v is None:
+        filled = fill_holes(fill_borders(u), fill_borders(v))
+        if filled is None:
             return None
+        u, v = filled
     u = np.flip(u, axis=0) * scale / dt * 1000
     v = -np.flip(v, axis=0) * scale / dt * 1000
     return x * scale, y * scale, u, v
