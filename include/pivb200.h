@@ -133,6 +133,29 @@ int pivb200_shift_dws(const uint8_t* frame, int H, int W, const int64_t* grid, l
                       uint8_t* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * On-device field post-processing (additive; the reference has no device counterpart -- it fills
+ * holes on the host with SciPy Delaunay interpolation, PB:266-344 + 884-892, and keeps its running
+ * statistics in workers.py:79-119).  Fields are float64 [n_pairs][n_rows][n_cols].
+ *
+ * pivb200_nmt: normalised median test on the 3x3 neighbourhood (neighbours flagged in `mask` are
+ *   ignored; `mask` may be NULL).  outlier[g] = mask[g] | (|u - med(u_nb)| / (med|u_nb - med| + eps)
+ *   > threshold, same for v); vectors with fewer than two usable neighbours are not tested.
+ *   `outlier` must not alias `mask`.
+ * pivb200_replace: vectors flagged in `invalid` become the median of their usable 3x3 neighbours;
+ *   Jacobi sweeps (at most max_sweeps, rounded up to even) let holes fill from the rim inwards;
+ *   `invalid` is cleared where a value was produced; vectors never reached become 0 and stay
+ *   flagged.  In place; `workspace` is pivb200_replace_workspace_bytes(...) bytes, 8-byte aligned.
+ * pivb200_stats_accumulate: sums[5][n_rows][n_cols] += sum over the batch's pairs of
+ *   (u, v, u*u, v*v, u*v) -- the streaming form of workers.py:85-95's stacked arrays. */
+int pivb200_nmt(const double* u, const double* v, const uint8_t* mask, int n_pairs, int n_rows,
+                int n_cols, double threshold, double eps, uint8_t* outlier, void* stream);
+long long pivb200_replace_workspace_bytes(int n_pairs, int n_rows, int n_cols);
+int pivb200_replace(double* u, double* v, uint8_t* invalid, int n_pairs, int n_rows, int n_cols,
+                    int max_sweeps, void* workspace, void* stream);
+int pivb200_stats_accumulate(const double* u, const double* v, int n_pairs, int n_rows, int n_cols,
+                             double* sums, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): sustained FP32 FFMA throughput of the current device in
  * TFLOP/s (2 flops per FFMA), timed with CUDA events over `iters` launches.  HOST pointer. */
 int pivb200_measure_fp32_peak(int iters, double* tflops_host, void* stream);

@@ -42,6 +42,11 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_void_p]),
     "pivb200_shift_dws": (c_int, [c_void_p, c_int, c_int, c_void_p, c_longlong, c_int, c_void_p,
                                   c_void_p, c_void_p, c_void_p]),
+    "pivb200_nmt": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double, c_void_p,
+                            c_void_p]),
+    "pivb200_replace_workspace_bytes": (c_longlong, [c_int, c_int, c_int]),
+    "pivb200_replace": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pivb200_stats_accumulate": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "pivb200_measure_fp32_peak": (c_int, [c_int, POINTER(c_double), c_void_p]),
     "pivb200_launch_count": (c_longlong, []),
 }

@@ -22,7 +22,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from .dataset import PIVDataset, ToTensor, natural_keys  # noqa: F401  (re-exported)
+from .dataset import (PIVDataset, ToTensor, natural_keys, plan_batches, read_gray,  # noqa: F401
+                      shard_range)
 from .engine import PIVPlan, pass_schedule
 from .geometry import get_coordinates, get_field_shape, spline_operator  # noqa: F401
 from .postprocess import finalize_field
@@ -305,11 +306,24 @@ class OfflinePIV:
     float64 ``[n_rows, n_cols]`` arrays of the LAST pass grid: coordinates in mm
     (``px * scale``) and velocities in m/s (``px * scale / dt * 1000``, dt in microseconds),
     rows flipped and v negated exactly like the reference.  Pairs are skipped when an image
-    cannot be read or when the hole filling declines (see postprocess.fill_holes)."""
+    cannot be read or when the hole filling declines (see postprocess.fill_holes).
+
+    Keyword-only extensions (the reference processes one pair at a time on one device):
+
+    ``batch_pairs``     pairs per kernel launch / H2D copy (default 8)
+    ``decode_threads``  image-decoding threads that fill the pinned staging memory (default 4)
+    ``shard``           ``(rank, world)``: this object processes only its contiguous block of the pair
+                        list (one process per GPU, no collective; see dataset.shard_range).  ``len()``
+                        is then the block's length and ``pair_indices`` the global pair numbers.
+    ``replace``         ``"reference"`` (default): host hole filling exactly like the reference
+                        (SciPy Delaunay); ``"stencil"``: on-device 3x3 replacement, see
+                        postprocess_device.py (a documented deviation; never skips a pair)."""
 
     def __init__(self, folder: str, device: str, file_fmt: str, wind_size: int, overlap: int,
                  multipass: int = 1, multipass_mode: str = "CWS", dt: int = 1, scale: float = 1.,
-                 multipass_scale: float = 2., folder_mode: str = "pairs") -> None:
+                 multipass_scale: float = 2., folder_mode: str = "pairs", *, batch_pairs: int = 8,
+                 decode_threads: int = 4, shard: Optional[Tuple[int, int]] = None,
+                 replace: str = "reference") -> None:
         self._wind_size = wind_size
         self._overlap = overlap
         self._dt = dt
@@ -320,12 +334,19 @@ class OfflinePIV:
         self._dataset = PIVDataset(folder, file_fmt, folder_mode, transform=None)
         self._iter_function = IterModMap.functions[multipass_mode]   # KeyError for unknown modes
         self._mode = multipass_mode
+        if replace not in ("reference", "stencil"):
+            raise KeyError(replace)
+        self._replace = replace
+        self._batch_pairs = max(1, int(batch_pairs))
+        self._decode_threads = max(1, int(decode_threads))
+        rank, world = shard if shard is not None else (0, 1)
+        self.pair_indices = shard_range(len(self._dataset), rank, world)
         self._plan = None
         self._pipe = None
         if not len(self):
             return
         self._device = _cuda_device(self._device)
-        frame_a, _ = self._dataset[0]
+        frame_a, _ = self._dataset[self.pair_indices.start]
         if frame_a is not None:
             self._plan = self._make_plan(frame_a.shape)
 
@@ -334,39 +355,82 @@ class OfflinePIV:
                        self._iter_scale, device=self._device)
 
     def __len__(self) -> int:
-        return len(self._dataset)
+        return len(self.pair_indices)
+
+    # -- decoding ------------------------------------------------------------------------------
+    def _decode_into(self, path: str, dst: np.ndarray) -> bool:
+        """Decode one frame straight into pinned staging memory; False = unreadable / wrong shape."""
+        img = read_gray(path)
+        if img is None:
+            return False
+        if self._plan is None:
+            return False
+        if img.shape != dst.shape:
+            print(f"Warning! {path}: frame shape {img.shape} != {dst.shape}, pair skipped")
+            return False
+        np.copyto(dst, img)
+        return True
+
+    def _ensure_plan(self, batches) -> bool:
+        """The constructor could not read the first frame: find the first readable one."""
+        if self._plan is not None:
+            return True
+        for batch in batches:
+            for path in batch.files:
+                img = read_gray(path)
+                if img is not None:
+                    self._plan = self._make_plan(img.shape)
+                    return True
+        return False
 
     def __call__(self) -> Generator:
-        """Yield ``(x, y, u, v)`` per processed pair, in pair order.  Image decoding runs two pairs
-        ahead on a helper thread (OpenCV releases the GIL) while the GPU works on the current one."""
-        from concurrent.futures import ThreadPoolExecutor
-        n = len(self._dataset)
-        if n == 0:
-            return
-        with ThreadPoolExecutor(max_workers=2) as pool:
-            ahead = [pool.submit(self._dataset.__getitem__, i) for i in range(min(2, n))]
-            for index in range(n):
-                a, b = ahead.pop(0).result()
-                if index + 2 < n:
-                    ahead.append(pool.submit(self._dataset.__getitem__, index + 2))
-                if a is None or b is None:
-                    continue
-                out = self._process(a, b)
-                if out is None:
-                    continue
-                yield out
+        """Yield ``(x, y, u, v)`` per processed pair, in pair order.
 
-    def _process(self, a: np.ndarray, b: np.ndarray):
-        """One decoded pair -> (x, y, u, v) or None (pair skipped, see postprocess.fill_holes)."""
-        if self._plan is None or (self._plan.H, self._plan.W) != a.shape:
-            self._plan = self._make_plan(a.shape)
-            self._pipe = None
-        if getattr(self, "_pipe", None) is None:
-            from .engine import HostPipeline
-            self._pipe = HostPipeline(self._plan, 1)
-            self._pin = [torch.empty((1,) + tuple(a.shape), dtype=torch.uint8).pin_memory() for _ in range(2)]
-        self._pin[0][0].copy_(torch.from_numpy(a))
-        self._pin[1][0].copy_(torch.from_numpy(b))
-        u, v, val = self._pipe.result(self._pipe.submit(self._pin[0], self._pin[1]))
+        Three stages overlap: ``decode_threads`` workers decode the frames of batch i+1 into pinned
+        memory (OpenCV releases the GIL) while the GPU runs batch i (one H2D of the unique frames, the
+        fused passes, one D2H of u, v, mask) and the caller's thread post-processes batch i-1."""
+        from concurrent.futures import ThreadPoolExecutor
+        from .engine import FramePipeline
+        batches = plan_batches(self._dataset.img_pairs, self._batch_pairs, self.pair_indices)
+        if not batches or not self._ensure_plan(batches):
+            return
+        if self._pipe is None or self._pipe.plan is not self._plan:
+            self._pipe = FramePipeline(self._plan, self._batch_pairs)
+        pipe = self._pipe
         geo = self._plan.out_geometry
-        return finalize_field(u[0].copy(), v[0].copy(), geo.x, geo.y, val[0], self._scale, self._dt)
+
+        with ThreadPoolExecutor(max_workers=self._decode_threads) as pool:
+            def stage(n):
+                frames = pipe.host_frames(n & 1)
+                return [pool.submit(self._decode_into, path, frames[j])
+                        for j, path in enumerate(batches[n].files)]
+
+            def finish(n, ok):
+                """Results of batch n -> finished fields of its readable pairs, in order."""
+                u, v, bad = pipe.result(n & 1)
+                batch = batches[n]
+                for i in range(len(batch)):
+                    if not (ok[batch.index_a[i]] and ok[batch.index_b[i]]):
+                        continue
+                    out = self._finalize(u[i].copy(), v[i].copy(), geo, bad[i])
+                    if out is not None:
+                        yield out
+
+            decoding = stage(0)
+            previous = None                       # (batch number, ok flags) in flight on the GPU
+            for n, batch in enumerate(batches):
+                ok = [f.result() for f in decoding]
+                pipe.submit(n & 1, len(batch), batch.chained)
+                if n + 1 < len(batches):
+                    # slot (n + 1) & 1 was used by batch n - 1, whose upload has long finished
+                    decoding = stage(n + 1)
+                if previous is not None:
+                    yield from finish(*previous)
+                previous = (n, ok)
+            yield from finish(*previous)
+
+    def _finalize(self, u, v, geo, invalid):
+        if self._replace == "stencil":
+            from .postprocess_device import finalize_field_stencil
+            return finalize_field_stencil(u, v, geo.x, geo.y, invalid, self._scale, self._dt)
+        return finalize_field(u, v, geo.x, geo.y, invalid, self._scale, self._dt)

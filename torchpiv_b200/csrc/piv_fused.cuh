@@ -192,12 +192,16 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return max(lo, mi
 struct WinGeo {
     int pair, r0, c0;
 };
+__device__ __forceinline__ int fast_div(const FastDiv& d, int n) {
+    const uint32_t un = static_cast<uint32_t>(n), t = __umulhi(d.M, un);
+    return static_cast<int>((t + ((un - t) >> d.s1)) >> d.s2);
+}
 __device__ __forceinline__ WinGeo window_geo(const PassParams& p, int g) {
     const int n = p.n_rows * p.n_cols;
     WinGeo w;
-    w.pair = g / n;
+    w.pair = fast_div(p.div_n, g);
     const int loc = g - w.pair * n;
-    const int wr = loc / p.n_cols;
+    const int wr = fast_div(p.div_c, loc);
     w.r0 = wr * p.step;
     w.c0 = (loc - wr * p.n_cols) * p.step;
     return w;
@@ -520,6 +524,8 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                     const TileDesc* desc = reinterpret_cast<const TileDesc*>(smem + S::TD_OFF);
                     const int d = desc[wi * 2 + frame].d;
                     uint32_t w0[W / 4], w1[W / 4];
+                    // (a uniform switch over the word part of d with statically addressed registers instead
+                    // of the select network was measured: no gain -- the loader is latency, not issue bound)
                     load_row_words<W, LOADER, W / 4>(region, l, d, w0);
                     load_row_words<W, LOADER, W / 4>(region, l + HALF, d, w1);
                     static_for<0, W>([&](auto jc) {

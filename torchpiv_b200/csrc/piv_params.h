@@ -17,6 +17,22 @@ enum Sink : int {
     SK_WIN = 2          // the (shifted) windows themselves [N, w, w] float32 (parity of the loader)
 };
 
+// Unsigned division by a run-time invariant (Granlund-Montgomery): q = (t + ((n - t) >> s1)) >> s2 with
+// t = umulhi(M, n); exact for every 32-bit n.  Replaces the ~40-instruction emulated integer division
+// in the per-job window geometry.
+struct FastDiv {
+    uint32_t M, s1, s2;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;                       // ceil(log2 d)
+    f.M = static_cast<uint32_t>(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    f.s1 = l < 1 ? l : 1;
+    f.s2 = l > 1 ? l - 1 : 0;
+    return f;
+}
+
 struct PassParams {
     // frames: pair p of frame a starts at fa + p * pair_stride (bytes); rows are `pitch` bytes apart
     const unsigned char* fa;
@@ -24,6 +40,7 @@ struct PassParams {
     long long pair_stride;
     int H, Wf, pitch;
     int n_rows, n_cols, step;        // window grid of one pair, window origin = (r*step, c*step)
+    FastDiv div_n, div_c;            // division by n_rows * n_cols and by n_cols
     long long n_total;               // n_pairs * n_rows * n_cols (or number of explicit windows)
     int first_pass;                  // 1: eps scaled by mean(a)*mean(b) and black-window rule (PB:513-514)
     const float* sxf;                // CWS shift per window (+ for frame b, - for frame a)

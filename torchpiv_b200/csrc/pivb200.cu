@@ -108,6 +108,8 @@ static int run_frame_pass(const uint8_t* fa, const uint8_t* fb, int n_pairs, lon
     p.n_cols = n_cols;
     p.step = wind - overlap;
     p.n_total = static_cast<long long>(n_rows) * n_cols * n_pairs;
+    p.div_n = make_fastdiv(static_cast<uint32_t>(n_rows) * static_cast<uint32_t>(n_cols));
+    p.div_c = make_fastdiv(static_cast<uint32_t>(n_cols));
     CUtensorMap ta, tb;
     memset(&ta, 0, sizeof(ta));
     memset(&tb, 0, sizeof(tb));

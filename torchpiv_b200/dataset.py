@@ -12,7 +12,8 @@ from typing import List, Tuple
 
 import numpy as np
 
-__all__ = ["natural_keys", "list_pairs", "read_gray", "PIVDataset", "ToTensor"]
+__all__ = ["natural_keys", "list_pairs", "read_gray", "PIVDataset", "ToTensor", "shard_range",
+           "FrameBatch", "plan_batches"]
 
 _DIGITS = re.compile(r"(\d+)")
 
@@ -74,3 +75,59 @@ class PIVDataset:
         if self.transform:
             return self.transform(frame_a), self.transform(frame_b)
         return frame_a, frame_b
+
+
+# --------------------------------------------------------------------------------------------
+# Batching and sharding of the pair list (no reference counterpart:
+# the reference decodes and processes one pair at a time on one device, PIVbackend.py:862-903)
+# --------------------------------------------------------------------------------------------
+def shard_range(n_items: int, rank: int, world: int) -> range:
+    """Contiguous block of ``range(n_items)`` owned by ``rank`` of ``world`` (block sizes differ by
+    at most one).  Contiguous blocks keep consecutive pairs on one GPU, so ``sequential`` folders
+    decode and upload every frame once per shard instead of twice."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world of {world}")
+    base, extra = divmod(int(n_items), world)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+class FrameBatch:
+    """One batch of pairs as the frames to decode and where each pair finds its two frames.
+
+    ``files``   unique frame files of the batch, in upload order
+    ``index_a`` / ``index_b``  position in ``files`` of frame a / b of every pair
+    ``chained`` True when pair i's frame b is pair i+1's frame a for the whole batch (sequential
+                folders): the frames are then uploaded ONCE as ``[K+1, H, W]`` and the two frame
+                stacks the kernels read are the overlapping views ``[0:K]`` and ``[1:K+1]``."""
+
+    def __init__(self, first_pair: int, pairs):
+        self.first_pair = int(first_pair)
+        self.pairs = list(pairs)
+        k = len(self.pairs)
+        self.chained = k > 0 and all(self.pairs[i][1] == self.pairs[i + 1][0] for i in range(k - 1))
+        if self.chained:
+            self.files = [p[0] for p in self.pairs] + [self.pairs[-1][1]]
+            self.index_a = list(range(k))
+            self.index_b = list(range(1, k + 1))
+        else:
+            # frames a first, then frames b: both stacks are contiguous blocks of the upload
+            self.files = [p[0] for p in self.pairs] + [p[1] for p in self.pairs]
+            self.index_a = list(range(k))
+            self.index_b = list(range(k, 2 * k))
+
+    def __len__(self) -> int:
+        return len(self.pairs)
+
+
+def plan_batches(pairs, batch_pairs: int, indices=None):
+    """Split the pair list (or the sub-range ``indices`` of it, e.g. a :func:`shard_range`) into
+    :class:`FrameBatch` es of at most ``batch_pairs`` consecutive pairs."""
+    if batch_pairs < 1:
+        raise ValueError("batch_pairs must be >= 1")
+    idx = range(len(pairs)) if indices is None else indices
+    out = []
+    for s in range(idx.start, idx.stop, batch_pairs):
+        e = min(s + batch_pairs, idx.stop)
+        out.append(FrameBatch(s, [pairs[i] for i in range(s, e)]))
+    return out

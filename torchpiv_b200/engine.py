@@ -20,7 +20,7 @@ import torch
 from . import _lib
 from .geometry import SUPPORTED_WINDOWS, get_coordinates, get_field_shape, spline_operator
 
-__all__ = ["PassGeometry", "PIVPlan", "pass_schedule"]
+__all__ = ["PassGeometry", "PIVPlan", "pass_schedule", "HostPipeline", "FramePipeline"]
 
 
 @dataclass
@@ -245,3 +245,72 @@ class HostPipeline:
         s["done"].synchronize()
         B = s["n"]
         return s["u"][:B].numpy(), s["v"][:B].numpy(), s["m"][:B].numpy().astype(bool)
+
+
+class FramePipeline:
+    """Batches of pairs from pinned host FRAME stacks (the ``OfflinePIV`` data path).
+
+    A slot holds up to ``2 * batch_pairs`` frames on the host (pinned; image decoders write straight
+    into it) and on the device.  ``submit`` uploads only the frames a batch really has -- ``K + 1``
+    for a chained (sequential-folder) batch, whose two frame stacks are the overlapping device views
+    ``[0:K]`` and ``[1:K+1]``, else ``2 K`` -- on the copy stream, runs the plan on the compute stream
+    and brings ``u, v, mask`` back; two slots alternate so that decoding / upload of batch i+1
+    overlaps the kernels of batch i."""
+
+    def __init__(self, plan: PIVPlan, batch_pairs: int):
+        self.plan = plan
+        dev = plan.device
+        g = plan.out_geometry
+        K = self.batch_pairs = int(batch_pairs)
+        self.compute = torch.cuda.Stream(dev)
+        self.copy = torch.cuda.Stream(dev)
+        self.slots = []
+        for _ in range(2):
+            self.slots.append({
+                "host": torch.empty((2 * K, plan.H, plan.W), dtype=torch.uint8).pin_memory(),
+                "dev": torch.empty((2 * K, plan.H, plan.W), dtype=torch.uint8, device=dev),
+                "u": torch.empty((K, g.n_rows, g.n_cols), dtype=torch.float64).pin_memory(),
+                "v": torch.empty((K, g.n_rows, g.n_cols), dtype=torch.float64).pin_memory(),
+                "m": torch.empty((K, g.n_rows, g.n_cols), dtype=torch.uint8).pin_memory(),
+                "uploaded": torch.cuda.Event(), "done": torch.cuda.Event(), "n": 0,
+            })
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def host_frames(self, sid: int) -> np.ndarray:
+        """Writable ``[2K, H, W]`` uint8 view of slot ``sid``'s pinned staging memory.  Blocks until
+        the previous upload out of this slot has finished."""
+        s = self.slots[sid]
+        s["uploaded"].synchronize()
+        return s["host"].numpy()
+
+    def submit(self, sid: int, n_pairs: int, chained: bool) -> None:
+        K = int(n_pairs)
+        if not 0 < K <= self.batch_pairs:
+            raise ValueError("batch larger than the pipeline was built for")
+        s = self.slots[sid]
+        n_frames = K + 1 if chained else 2 * K
+        with torch.cuda.stream(self.copy):
+            self.copy.wait_event(s["done"])        # the kernels of the slot's previous batch have read it
+            s["dev"][:n_frames].copy_(s["host"][:n_frames], non_blocking=True)
+            s["uploaded"].record(self.copy)
+        fa = s["dev"][:K]
+        fb = s["dev"][1:K + 1] if chained else s["dev"][K:2 * K]
+        with torch.cuda.stream(self.compute):
+            self.compute.wait_event(s["uploaded"])
+            u, v, m = self.plan.run(fa, fb, stream=self.compute.cuda_stream)
+            s["u"][:K].copy_(u, non_blocking=True)
+            s["v"][:K].copy_(v, non_blocking=True)
+            s["m"][:K].copy_(m, non_blocking=True)
+            s["done"].record(self.compute)
+        s["n"] = K
+        self.h2d_bytes += n_frames * self.plan.H * self.plan.W
+        self.d2h_bytes += K * (s["u"][0].numel() * 16 + s["m"][0].numel())
+
+    def result(self, sid: int):
+        """``(u, v, invalid)`` NumPy arrays of the slot's batch (views, valid until the slot is
+        submitted again)."""
+        s = self.slots[sid]
+        s["done"].synchronize()
+        K = s["n"]
+        return s["u"][:K].numpy(), s["v"][:K].numpy(), s["m"][:K].numpy().astype(bool)
