@@ -145,15 +145,17 @@ int pivb200_shift_dws(const uint8_t* frame, int H, int W, const int64_t* grid, l
  *   Jacobi sweeps (at most max_sweeps, rounded up to even) let holes fill from the rim inwards;
  *   `invalid` is cleared where a value was produced; vectors never reached become 0 and stay
  *   flagged.  In place; `workspace` is pivb200_replace_workspace_bytes(...) bytes, 8-byte aligned.
- * pivb200_stats_accumulate: sums[5][n_rows][n_cols] += sum over the batch's pairs of
- *   (u, v, u*u, v*v, u*v) -- the streaming form of workers.py:85-95's stacked arrays. */
+ * pivb200_stats_accumulate: running moments[5][n_rows][n_cols] of the fields seen so far -- mean u,
+ *   mean v, then the sums of (u-mean_u)^2, (v-mean_v)^2, (u-mean_u)(v-mean_v) -- are merged with this
+ *   batch (pairwise update, free of the cancellation of raw power sums).  `n_before` = number of fields
+ *   already merged (0 with a zeroed buffer).  The streaming form of workers.py:79-95's stacked arrays. */
 int pivb200_nmt(const double* u, const double* v, const uint8_t* mask, int n_pairs, int n_rows,
                 int n_cols, double threshold, double eps, uint8_t* outlier, void* stream);
 long long pivb200_replace_workspace_bytes(int n_pairs, int n_rows, int n_cols);
 int pivb200_replace(double* u, double* v, uint8_t* invalid, int n_pairs, int n_rows, int n_cols,
                     int max_sweeps, void* workspace, void* stream);
 int pivb200_stats_accumulate(const double* u, const double* v, int n_pairs, int n_rows, int n_cols,
-                             double* sums, void* stream);
+                             long long n_before, double* moments, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): sustained FP32 FFMA throughput of the current device in

@@ -162,12 +162,66 @@ def gen_offline():
         shutil.rmtree(tmp)
 
 
+def _worker_statistics_source():
+    """The statistics block of the reference's PIVWorker.run (workers.py: from `if u_inst:` to the end
+    of the `table = {...}` literal), read from /root/reference at generation time and dedented.  The
+    worker module itself cannot be imported (Qt thread classes); its numerics are plain NumPy."""
+    import textwrap
+    path = os.path.join(ref_loader.REF_ROOT, "workers.py")
+    lines = open(path).read().splitlines()
+    start = next(i for i, ln in enumerate(lines) if ln.strip() == "if u_inst:")
+    end = next(i for i in range(start, len(lines)) if lines[i].strip() == "}" and "table" in "".join(lines[start:i]))
+    return textwrap.dedent("\n".join(lines[start:end + 1]))
+
+
+def gen_statistics():
+    import types
+    rng = np.random.default_rng(7)
+    out = {}
+    for tag, (nr, nc, n, scale) in {"a": (9, 13, 6, 0.02), "b": (17, 21, 3, 1.0)}.items():
+        xs, ys = np.meshgrid((np.arange(nc) * 16.0 + 16.0) * scale, (np.arange(nr) * 16.0 + 16.0) * scale)
+        u_list = [rng.normal(3.0, 1.0, (nr, nc)) + 0.05 * xs for _ in range(n)]
+        v_list = [rng.normal(-2.0, 0.5, (nr, nc)) - 0.03 * ys * xs for _ in range(n)]
+        sink = types.SimpleNamespace(emit=lambda *_: None)
+        ns = {"np": np, "x": xs, "y": ys, "u_inst": list(u_list), "v_inst": list(v_list),
+              "self": types.SimpleNamespace(progress=sink, avg_u=None, avg_v=None)}
+        exec(_worker_statistics_source(), ns)
+        out[f"{tag}_sha"] = np.array(cases.sha(xs, ys, *u_list, *v_list))
+        out[f"{tag}_x"], out[f"{tag}_y"] = xs, ys
+        out[f"{tag}_u"], out[f"{tag}_v"] = np.stack(u_list), np.stack(v_list)
+        out[f"{tag}_keys"] = np.array(list(ns["table"].keys()))
+        out[f"{tag}_table"] = np.stack(list(ns["table"].values()))
+    save("statistics.npz", **out)
+
+
+def gen_output_formats():
+    PF = sys.modules["torchPIV.PlotterFunctions"]
+    rng = np.random.default_rng(11)
+    data = {"x[mm]": rng.uniform(0, 40, (5, 7)), "y[mm]": rng.uniform(0, 40, (5, 7)),
+            "Vx[m/s]": rng.normal(0, 3, (5, 7)), "Vy[m/s]": rng.normal(0, 1e-4, (5, 7))}
+    tmp = tempfile.mkdtemp(prefix="pivgold_")
+    try:
+        d = os.path.join(tmp, "out")
+        for _ in range(3):      # the second and third call exercise the " (n)" numbering
+            PF.save_table("run_pair.txt", d, {k: v.copy() for k, v in data.items()})
+            PF.save_binary("run_pair.npy", d, {k: v.copy() for k, v in data.items()})
+        names = sorted(os.listdir(d))
+        out = {"names": np.array(names), "keys": np.array(list(data.keys())),
+               "values": np.stack(list(data.values()))}
+        for n in names:
+            out["file_" + n] = np.frombuffer(open(os.path.join(d, n), "rb").read(), dtype=np.uint8)
+        save("output_formats.npz", **out)
+    finally:
+        shutil.rmtree(tmp)
+
+
+GENERATORS = {"pass1": gen_pass1, "multipass": gen_multipass, "shift": gen_shift, "corr2disp": gen_corr2disp,
+              "offline": gen_offline, "statistics": gen_statistics, "output_formats": gen_output_formats}
+
 if __name__ == "__main__":
-    gen_pass1()
-    gen_multipass()
-    gen_shift()
-    gen_corr2disp()
-    gen_offline()
+    # no arguments: regenerate everything; otherwise only the named fixtures
+    for name in (sys.argv[1:] or list(GENERATORS)):
+        GENERATORS[name]()
     import scipy
     meta = {"torch": torch.__version__, "numpy": np.__version__, "scipy": scipy.__version__,
             "reference": "NikNazarov/TorchPIV src/torchPIV/PIVbackend.py (unmodified, device=cpu)",

@@ -46,7 +46,7 @@ SIGNATURES = {
                             c_void_p]),
     "pivb200_replace_workspace_bytes": (c_longlong, [c_int, c_int, c_int]),
     "pivb200_replace": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "pivb200_stats_accumulate": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pivb200_stats_accumulate": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_longlong, c_void_p, c_void_p]),
     "pivb200_measure_fp32_peak": (c_int, [c_int, POINTER(c_double), c_void_p]),
     "pivb200_launch_count": (c_longlong, []),
 }

@@ -317,13 +317,17 @@ class OfflinePIV:
                         is then the block's length and ``pair_indices`` the global pair numbers.
     ``replace``         ``"reference"`` (default): host hole filling exactly like the reference
                         (SciPy Delaunay); ``"stencil"``: on-device 3x3 replacement, see
-                        postprocess_device.py (a documented deviation; never skips a pair)."""
+                        postprocess_device.py (a documented deviation; never skips a pair);
+                        ``"stencil+nmt"``: a normalised median test first widens the invalid set.
+    ``statistics``      (stencil modes only) accumulate the running sums of the reference worker's
+                        statistics (workers.py:79-119) on the device; ``statistics_table()`` returns
+                        the table after the run."""
 
     def __init__(self, folder: str, device: str, file_fmt: str, wind_size: int, overlap: int,
                  multipass: int = 1, multipass_mode: str = "CWS", dt: int = 1, scale: float = 1.,
                  multipass_scale: float = 2., folder_mode: str = "pairs", *, batch_pairs: int = 8,
                  decode_threads: int = 4, shard: Optional[Tuple[int, int]] = None,
-                 replace: str = "reference") -> None:
+                 replace: str = "reference", statistics: bool = False) -> None:
         self._wind_size = wind_size
         self._overlap = overlap
         self._dt = dt
@@ -334,9 +338,13 @@ class OfflinePIV:
         self._dataset = PIVDataset(folder, file_fmt, folder_mode, transform=None)
         self._iter_function = IterModMap.functions[multipass_mode]   # KeyError for unknown modes
         self._mode = multipass_mode
-        if replace not in ("reference", "stencil"):
+        if replace not in ("reference", "stencil", "stencil+nmt"):
             raise KeyError(replace)
+        if statistics and replace == "reference":
+            raise ValueError("device statistics need the fields complete on the device: use replace='stencil'")
         self._replace = replace
+        self._want_stats = bool(statistics)
+        self.statistics = None
         self._batch_pairs = max(1, int(batch_pairs))
         self._decode_threads = max(1, int(decode_threads))
         rank, world = shard if shard is not None else (0, 1)
@@ -395,7 +403,14 @@ class OfflinePIV:
         if not batches or not self._ensure_plan(batches):
             return
         if self._pipe is None or self._pipe.plan is not self._plan:
-            self._pipe = FramePipeline(self._plan, self._batch_pairs)
+            post = None
+            if self._replace != "reference":
+                from .postprocess_device import FieldStatistics, StencilPost
+                g = self._plan.out_geometry
+                post = StencilPost(nmt=self._replace.endswith("nmt"), max_sweeps=max(g.n_rows, g.n_cols))
+                if self._want_stats:
+                    self.statistics = FieldStatistics(g.n_rows, g.n_cols, self._plan.device)
+            self._pipe = FramePipeline(self._plan, self._batch_pairs, post=post, stats=self.statistics)
         pipe = self._pipe
         geo = self._plan.out_geometry
 
@@ -420,7 +435,8 @@ class OfflinePIV:
             previous = None                       # (batch number, ok flags) in flight on the GPU
             for n, batch in enumerate(batches):
                 ok = [f.result() for f in decoding]
-                pipe.submit(n & 1, len(batch), batch.chained)
+                keep = [ok[batch.index_a[i]] and ok[batch.index_b[i]] for i in range(len(batch))]
+                pipe.submit(n & 1, len(batch), batch.chained, keep=keep)
                 if n + 1 < len(batches):
                     # slot (n + 1) & 1 was used by batch n - 1, whose upload has long finished
                     decoding = stage(n + 1)
@@ -429,8 +445,15 @@ class OfflinePIV:
                 previous = (n, ok)
             yield from finish(*previous)
 
+    def statistics_table(self) -> dict:
+        """The reference worker's statistics table (workers.py:100-119) of the pairs processed so far."""
+        if self.statistics is None:
+            raise ValueError("construct OfflinePIV with replace='stencil', statistics=True")
+        g = self._plan.out_geometry
+        return self.statistics.table(g.x, g.y, self._scale, self._dt)
+
     def _finalize(self, u, v, geo, invalid):
-        if self._replace == "stencil":
+        if self._replace != "reference":
             from .postprocess_device import finalize_field_stencil
             return finalize_field_stencil(u, v, geo.x, geo.y, invalid, self._scale, self._dt)
         return finalize_field(u, v, geo.x, geo.y, invalid, self._scale, self._dt)

@@ -1,7 +1,7 @@
 // Vector-field kernels that follow the fused correlation passes on the device:
 //   * normalised median test (outlier detection on the 3x3 neighbourhood)
 //   * 3x3 stencil replacement of invalid vectors (Jacobi sweeps, holes fill from their rim inwards)
-//   * streaming statistics of a sequence of fields (sums for mean / Reynolds stresses)
+//   * streaming statistics of a sequence of fields (running mean / Reynolds-stress moments)
 //
 // The reference has NO on-device counterpart: it validates by the peak ratio only and fills holes on
 // the host with SciPy's Delaunay interpolation (PB:266-344, 884-892); the running statistics live in
@@ -120,21 +120,32 @@ __global__ void zero_flagged_kernel(double* __restrict__ u, double* __restrict__
         if (bad[g]) { u[g] = 0.0; v[g] = 0.0; }
 }
 
-// sums[k][e] += over the pairs of this batch: k = 0..4 -> u, v, u*u, v*v, u*v
+// Running moments of a sequence of fields, merged batch by batch (Chan et al.'s pairwise update: no
+// cancellation, unlike raw power sums).  mom[0..1] = mean u, v; mom[2..4] = sums of (u-mean_u)^2,
+// (v-mean_v)^2, (u-mean_u)(v-mean_v) over the `n_before` fields seen so far.
 __global__ void stats_accumulate_kernel(const double* __restrict__ u, const double* __restrict__ v,
-                                        int n_pairs, int per, double* __restrict__ sums) {
+                                        int n_pairs, int per, double n_before, double* __restrict__ mom) {
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < per; e += gridDim.x * blockDim.x) {
-        double su = 0, sv = 0, suu = 0, svv = 0, suv = 0;
+        double mu = 0, mv = 0;
         for (int p = 0; p < n_pairs; ++p) {
-            const double a = u[static_cast<long long>(p) * per + e], b = v[static_cast<long long>(p) * per + e];
-            su += a; sv += b;
+            mu += u[static_cast<long long>(p) * per + e];
+            mv += v[static_cast<long long>(p) * per + e];
+        }
+        const double nb = static_cast<double>(n_pairs);
+        mu /= nb;
+        mv /= nb;
+        double suu = 0, svv = 0, suv = 0;
+        for (int p = 0; p < n_pairs; ++p) {        // second read of the batch: L2 hits
+            const double a = u[static_cast<long long>(p) * per + e] - mu, b = v[static_cast<long long>(p) * per + e] - mv;
             suu = fma(a, a, suu); svv = fma(b, b, svv); suv = fma(a, b, suv);
         }
-        sums[e] += su;
-        sums[per + e] += sv;
-        sums[2 * per + e] += suu;
-        sums[3 * per + e] += svv;
-        sums[4 * per + e] += suv;
+        const double n = n_before + nb, w = n_before * nb / n;
+        const double du = mu - mom[e], dv = mv - mom[per + e];
+        mom[e] += du * nb / n;
+        mom[per + e] += dv * nb / n;
+        mom[2 * per + e] += suu + du * du * w;
+        mom[3 * per + e] += svv + dv * dv * w;
+        mom[4 * per + e] += suv + du * dv * w;
     }
 }
 
@@ -191,12 +202,12 @@ int pivb200_replace(double* u, double* v, uint8_t* invalid, int n_pairs, int n_r
 }
 
 int pivb200_stats_accumulate(const double* u, const double* v, int n_pairs, int n_rows, int n_cols,
-                             double* sums, void* stream) {
-    if (!u || !v || !sums || n_pairs < 1 || n_rows < 1 || n_cols < 1) return PIVB200_E_ARG;
+                             long long n_before, double* moments, void* stream) {
+    if (!u || !v || !moments || n_pairs < 1 || n_rows < 1 || n_cols < 1 || n_before < 0) return PIVB200_E_ARG;
     const long long per = static_cast<long long>(n_rows) * n_cols;
     if (per >= (1ll << 31)) return PIVB200_E_SIZE;
     stats_accumulate_kernel<<<grid_of(per), kBlock, 0, static_cast<cudaStream_t>(stream)>>>(
-        u, v, n_pairs, static_cast<int>(per), sums);
+        u, v, n_pairs, static_cast<int>(per), static_cast<double>(n_before), moments);
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }

@@ -257,8 +257,12 @@ class FramePipeline:
     and brings ``u, v, mask`` back; two slots alternate so that decoding / upload of batch i+1
     overlaps the kernels of batch i."""
 
-    def __init__(self, plan: PIVPlan, batch_pairs: int):
+    def __init__(self, plan: PIVPlan, batch_pairs: int, post=None, stats=None):
         self.plan = plan
+        # post(u, v, mask, stream): in-place device post-processing between the last pass and the D2H
+        # copy (postprocess_device.StencilPost); stats: postprocess_device.FieldStatistics fed after it
+        self.post = post
+        self.stats = stats
         dev = plan.device
         g = plan.out_geometry
         K = self.batch_pairs = int(batch_pairs)
@@ -284,7 +288,9 @@ class FramePipeline:
         s["uploaded"].synchronize()
         return s["host"].numpy()
 
-    def submit(self, sid: int, n_pairs: int, chained: bool) -> None:
+    def submit(self, sid: int, n_pairs: int, chained: bool, keep=None) -> None:
+        """``keep``: optional per-pair flags; pairs flagged False (unreadable frames) are left out of
+        the statistics."""
         K = int(n_pairs)
         if not 0 < K <= self.batch_pairs:
             raise ValueError("batch larger than the pipeline was built for")
@@ -299,6 +305,14 @@ class FramePipeline:
         with torch.cuda.stream(self.compute):
             self.compute.wait_event(s["uploaded"])
             u, v, m = self.plan.run(fa, fb, stream=self.compute.cuda_stream)
+            if self.post is not None:
+                self.post(u, v, m, stream=self.compute.cuda_stream)
+            if self.stats is not None:
+                if keep is None or all(keep):
+                    self.stats.add(u, v, stream=self.compute.cuda_stream)
+                elif any(keep):
+                    sel = torch.tensor([i for i, k in enumerate(keep) if k], device=u.device)
+                    self.stats.add(u[sel], v[sel], stream=self.compute.cuda_stream)
             s["u"][:K].copy_(u, non_blocking=True)
             s["v"][:K].copy_(v, non_blocking=True)
             s["m"][:K].copy_(m, non_blocking=True)
