@@ -179,6 +179,45 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 
+// Reductions over the LANES lanes of one window.  A whole warp (64 px windows) takes one CREDUX
+// (redux.sync on f32 is new with sm_100a) instead of a five-level shuffle ladder; sub-warp groups keep
+// the ladder: redux.sync with per-group member masks is serialised group by group (WARPSYNC.EXCLUSIVE),
+// measured 30-60 % slower per pass on B200.
+template <int LANES>
+__device__ __forceinline__ float group_max(float v) {
+    if constexpr (LANES == 32) {
+        float r;
+        asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+        return r;
+    } else {
+#pragma unroll
+        for (int o = LANES / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+}
+template <int LANES>
+__device__ __forceinline__ float group_min(float v) {
+    if constexpr (LANES == 32) {
+        float r;
+        asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+        return r;
+    } else {
+#pragma unroll
+        for (int o = LANES / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+}
+template <int LANES>
+__device__ __forceinline__ int group_min_int(int v) {
+    if constexpr (LANES == 32) {
+        return __reduce_min_sync(0xffffffffu, v);
+    } else {
+#pragma unroll
+        for (int o = LANES / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+}
+
 // byte b of `word` as a float.  (A PRMT + FADD(-2^23) pair that avoids the quarter-rate XU pipe was
 // measured: -2 % for the 64 px pass, +3 % for the 32 px passes -- not kept.)
 __device__ __forceinline__ float u8f(uint32_t word, int b) {
@@ -378,7 +417,7 @@ __device__ __noinline__ void gather_border_tile(const PassParams& p, const TileD
 template <int W, int LOADER, int SINK>
 __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_kernel(const __grid_constant__ CUtensorMap tmA,
                                                        const __grid_constant__ CUtensorMap tmB,
-                                                       const PassParams p) {
+                                                       const __grid_constant__ PassParams p) {
     using G = Geo<W>;
     using T = Tile<W, LOADER>;
     using S = Smem<W, LOADER>;
@@ -401,8 +440,6 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
     const int njobs = (n_total + NW - 1) / NW;
     const int job_stride = gridDim.x * nwarps;
     const uint32_t bar = smem_u32(smem + S::BAR_OFF);
-    uint32_t parity = 0;
-    bool pending = false;
 
     uint32_t tpark = 0;                                      // TMEM address of this warp's parking area
     if constexpr (kTmem) {
@@ -461,18 +498,22 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                     gather_border_tile<W, LOADER>(p, dsc, smem + S::REG_OFF + w2 * G::REGION, frame, lane);
                 }
             }
-            if (tx != 0) {
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(bar, tx);
+            // The barrier is armed for EVERY (job, frame), also with tx == 0 (all tiles gathered: the phase
+            // completes at once), so its phase parity at the matching wait is simply `frame` -- no
+            // per-warp pending / parity state to keep (it used to be spilled to local memory).
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar, tx);
 #pragma unroll 1
-                    for (int w2 = 0; w2 < NW; ++w2) {
-                        const TileDesc dsc = desc[w2 * 2 + frame];
-                        if (dsc.d >= 0)
-                            tma_load_3d(smem_u32(smem + S::REG_OFF + w2 * G::REGION), frame ? &tmB : &tmA, bar,
-                                        dsc.ox & ~15, dsc.oy, dsc.pair);
+                for (int w2 = 0; w2 < NW; ++w2) {
+                    const TileDesc dsc = desc[w2 * 2 + frame];
+                    if (dsc.d >= 0) {
+                        // two call sites with the __grid_constant__ maps addressed statically: a selected
+                        // pointer makes the compiler copy both maps to the (local-memory) stack
+                        const uint32_t dst = smem_u32(smem + S::REG_OFF + w2 * G::REGION);
+                        if (frame) tma_load_3d(dst, &tmB, bar, dsc.ox & ~15, dsc.oy, dsc.pair);
+                        else tma_load_3d(dst, &tmA, bar, dsc.ox & ~15, dsc.oy, dsc.pair);
                     }
                 }
-                pending = true;
             }
             __syncwarp();
             // gathered tiles are stored from byte 0
@@ -480,14 +521,8 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
             __syncwarp();
         }
     };
-    auto stage_wait = [&]() {
-        if constexpr (T::kFrame) {
-            if (pending) {
-                mbar_wait(bar, parity);
-                parity ^= 1u;
-                pending = false;
-            }
-        }
+    auto stage_wait = [&](int frame) {
+        if constexpr (T::kFrame) mbar_wait(bar, static_cast<uint32_t>(frame));
     };
 
     // Every warp of the CTA runs the same number of iterations (optional block barriers inside keep the
@@ -513,13 +548,14 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
             if ((p.sync_mask >> s) & 1) {
                 // lock step (shared instruction fetch): the whole CTA, or groups of four warps (one per
                 // scheduler) so that different groups sit in different phases (FP vs shared-memory bound)
-                if (p.sync_group) asm volatile("bar.sync %0, 128;" ::"r"(1 + (warp >> 2)) : "memory");
+                if (p.sync_group == 1) asm volatile("bar.sync %0, 128;" ::"r"(1 + (warp >> 2)) : "memory");
+                else if (p.sync_group == 2) asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"((nwarps >> 2) * 32) : "memory");
                 else __syncthreads();
             }
             // ---------------------------------------------------------------- load
             if (s == 0 || s == 2) {
                 const int frame = s >> 1;
-                stage_wait();
+                stage_wait(frame);
                 if constexpr (LOADER == LD_FRAME_INT) {
                     const TileDesc* desc = reinterpret_cast<const TileDesc*>(smem + S::TD_OFF);
                     const int d = desc[wi * 2 + frame].d;
@@ -801,21 +837,19 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
 
         // =============================== epilogue ==========================================
         if constexpr (SINK == SK_DISP) {
-            float gmax = fmaxf(mx_hi, mx_lo), gmin = mn;
-#pragma unroll
-            for (int o = HALF / 2; o > 0; o >>= 1) {
-                gmax = fmaxf(gmax, __shfl_xor_sync(FULL, gmax, o));
-                gmin = fminf(gmin, __shfl_xor_sync(FULL, gmin, o));
+            // predictor glue operands of this window: requested now, consumed after the fit
+            double base_u = 0.0, base_v = 0.0, pred_u = 0.0, pred_v = 0.0;
+            if (l == 0 && g_valid) {
+                if (p.base_u) { base_u = p.base_u[g]; base_v = p.base_v[g]; }
+                if (p.pred_u) { pred_u = p.pred_u[g]; pred_v = p.pred_v[g]; }
             }
+            const float gmax = group_max<HALF>(fmaxf(mx_hi, mx_lo)), gmin = group_min<HALF>(mn);
             // first maximum in flat (row-major) order of the shifted map (torch argmax, PB:383)
             constexpr int BIG = 1 << 20;
-            int R = min(mx_lo == gmax ? l : BIG, mx_hi == gmax ? l + HALF : BIG);
-#pragma unroll
-            for (int o = HALF / 2; o > 0; o >>= 1) R = min(R, __shfl_xor_sync(FULL, R, o));
+            int R = group_min_int<HALF>(min(mx_lo == gmax ? l : BIG, mx_hi == gmax ? l + HALF : BIG));
             R = min(R, W - 1);      // only reachable with NaN input
-            int C = (mapw[R * PC + l] == gmax) ? l : ((mapw[R * PC + l + HALF] == gmax) ? l + HALF : BIG);
-#pragma unroll
-            for (int o = HALF / 2; o > 0; o >>= 1) C = min(C, __shfl_xor_sync(FULL, C, o));
+            int C = group_min_int<HALF>(
+                (mapw[R * PC + l] == gmax) ? l : ((mapw[R * PC + l + HALF] == gmax) ? l + HALF : BIG));
             C = min(C, W - 1);
             constexpr int N2 = W * W;
             const int m = R * W + C;
@@ -869,8 +903,7 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                         if (!in_patch) sp = fmaxf(sp, mapw[rr * PC + cc]);
                     }
                 }
-#pragma unroll
-                for (int o = HALF / 2; o > 0; o >>= 1) sp = fmaxf(sp, __shfl_xor_sync(FULL, sp, o));
+                sp = group_max<HALF>(sp);
                 const double c2 = (static_cast<double>(sp) - dmin) + eps;
                 const double rt = cm / c2;
                 invalid = rt < p.val_ratio;
@@ -884,13 +917,12 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                 ratio = 0.f;
             }
             if (l == 0 && g_valid) {
-                double uo = du + (p.base_u ? p.base_u[g] : 0.0);
-                double vo = dv + (p.base_v ? p.base_v[g] : 0.0);
+                double uo = du + base_u;
+                double vo = dv + base_v;
                 if (p.pred_u) {
                     // PB:731-738: reject where the correction exceeds a positive predictor, or invalid
-                    const double pu = p.pred_u[g], pv = p.pred_v[g];
-                    if ((du > pu && rint(pu) > 0.0) || invalid) uo = pu;
-                    if ((dv > pv && rint(pv) > 0.0) || invalid) vo = pv;
+                    if ((du > pred_u && rint(pred_u) > 0.0) || invalid) uo = pred_u;
+                    if ((dv > pred_v && rint(pred_v) > 0.0) || invalid) vo = pred_v;
                 }
                 p.u[g] = uo;
                 p.v[g] = vo;
