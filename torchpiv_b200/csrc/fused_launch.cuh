@@ -55,6 +55,7 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const PassPa
     static const int env_warps = [] { const char* e = getenv("PIVB200_NWARPS"); return e ? atoi(e) : 0; }();
     int nwarps = (env_warps > 0 && env_warps < S::NWARPS) ? env_warps : S::NWARPS;
     if (p.sync_group) nwarps &= ~3;
+    if (p.sync_group >= 4 && nwarps % p.sync_group != 0) p.sync_group = 1;     // groups of N warps need N | nwarps
     long long grid = (njobs + nwarps - 1) / nwarps;
     if (grid > sms) grid = sms;
     kern<<<static_cast<unsigned>(grid), nwarps * 32, S::CTA_BYTES, stream>>>(ta, tb, p);
@@ -66,6 +67,8 @@ template <int W>
 static int launch_w(int loader, int sink, const CUtensorMap& ta, const CUtensorMap& tb,
                     const PassParams& p, cudaStream_t stream) {
     if (sink == SK_DISP && loader == LD_FRAME_INT) return launch_one<W, LD_FRAME_INT, SK_DISP>(ta, tb, p, stream);
+    if (sink == SK_DISP && loader == LD_FRAME_ALN) return launch_one<W, LD_FRAME_ALN, SK_DISP>(ta, tb, p, stream);
+    if (sink == SK_WIN && loader == LD_FRAME_ALN) return launch_one<W, LD_FRAME_ALN, SK_WIN>(ta, tb, p, stream);
     if (sink == SK_DISP && loader == LD_FRAME_CWS) return launch_one<W, LD_FRAME_CWS, SK_DISP>(ta, tb, p, stream);
     if (sink == SK_WIN && loader == LD_FRAME_INT) return launch_one<W, LD_FRAME_INT, SK_WIN>(ta, tb, p, stream);
     if (sink == SK_WIN && loader == LD_FRAME_CWS) return launch_one<W, LD_FRAME_CWS, SK_WIN>(ta, tb, p, stream);

@@ -61,22 +61,25 @@ struct Geo {
 
 template <int W, int LOADER>
 struct Tile {
-    static constexpr bool kFrame = (LOADER == LD_FRAME_INT || LOADER == LD_FRAME_CWS);
+    static constexpr bool kFrame = (LOADER == LD_FRAME_INT || LOADER == LD_FRAME_CWS || LOADER == LD_FRAME_ALN);
+    static constexpr bool kAligned = (LOADER == LD_FRAME_ALN);
     // TMA box.  The global start address of a box row must be 16-byte aligned (an unaligned x
     // coordinate faults as "illegal instruction" on sm_100a), so the box starts at the window's
     // x origin rounded DOWN to 16 and is 16 bytes wider than the bytes that are used; the row
     // loader re-aligns in registers by d = origin & 15.
     static constexpr int USED = (LOADER == LD_FRAME_CWS) ? W + 1 : W;    // bytes of a row that are read
-    static constexpr int BX = W + 16;                                    // box bytes per row
+    static constexpr int BX = kAligned ? W : W + 16;                     // box bytes per row
     static constexpr int BY = (LOADER == LD_FRAME_CWS) ? W + 1 : W;      // box rows
-    static constexpr int SWZ = (BX == 32) ? 1 : 0;                       // TMA swizzle: 32B / none
+    static constexpr int SWZ = (BX == 32) ? 1 : ((BX == 64) ? 2 : 0);    // TMA swizzle: 32B / 64B / none
+    static constexpr int BASE_ALIGN = (SWZ == 2) ? 512 : 256;            // the swizzle is a function of the shared-memory address
     static constexpr int TX = BX * BY;
     static_assert(!kFrame || TX <= Geo<W>::REGION, "the tile is staged inside the window's buffer");
-    // byte offset of 16-byte chunk `chunk` of row `row`.  Row pitches of 80 / 48 bytes (and the
-    // 32-byte swizzle for 32) make 8 consecutive rows hit 8 distinct 16-byte bank groups, so the
+    // byte offset of 16-byte chunk `chunk` of row `row`.  Row pitches of 80 / 48 bytes (and the 32- / 64-byte
+    // swizzles for pitches 32 / 64) make 8 consecutive rows hit 8 distinct 16-byte bank groups, so the
     // per-lane LDS.128 row reads are bank-conflict free.
     __device__ static __forceinline__ int off(int row, int chunk) {
         if constexpr (SWZ == 1) return row * 32 + ((chunk ^ ((row >> 2) & 1)) << 4);
+        else if constexpr (SWZ == 2) return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
         else return row * BX + (chunk << 4);
     }
 };
@@ -88,6 +91,15 @@ __device__ __forceinline__ void load_row_words(const unsigned char* tile, int ro
                                                uint32_t (&out)[NOUT]) {
     using T = Tile<W, LOADER>;
     constexpr int NL = T::BX / 4;
+    if constexpr (T::kAligned) {
+        static_assert(NOUT == NL, "aligned tiles hold exactly the window");
+        static_for<0, T::BX / 16>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            const uint4 q = *reinterpret_cast<const uint4*>(tile + T::off(row, c));
+            out[4 * c] = q.x; out[4 * c + 1] = q.y; out[4 * c + 2] = q.z; out[4 * c + 3] = q.w;
+        });
+        return;
+    }
     uint32_t L[NL + 3];
     static_for<0, T::BX / 16>([&](auto cc) {
         constexpr int c = decltype(cc)::value;
@@ -119,7 +131,8 @@ struct Smem {
     static constexpr int TD = T::kFrame ? G::NW * 2 * 32 : 0;
     static constexpr int BAR_OFF = ((TD_OFF + TD + 7) / 8) * 8;
     static constexpr int TOTAL = BAR_OFF + 8;
-    static constexpr int STRIDE = ((TOTAL + 255) / 256) * 256;
+    static constexpr int STRIDE = ((TOTAL + T::BASE_ALIGN - 1) / T::BASE_ALIGN) * T::BASE_ALIGN;
+    static_assert(G::NW == 1 || T::BASE_ALIGN <= 256, "window buffers are 256-byte aligned inside a warp's slot");
     static constexpr int SMEM_MAX = 232448 - 1024;    // 227 KB opt-in limit per CTA minus the static allocation
     // warps per CTA: bounded by shared memory, by the register file (launch bounds) and by the 512
     // TMEM columns (4 lane quarters x 512 / TCOLS warps)
@@ -550,13 +563,14 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                 // scheduler) so that different groups sit in different phases (FP vs shared-memory bound)
                 if (p.sync_group == 1) asm volatile("bar.sync %0, 128;" ::"r"(1 + (warp >> 2)) : "memory");
                 else if (p.sync_group == 2) asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"((nwarps >> 2) * 32) : "memory");
+                else if (p.sync_group >= 4) asm volatile("bar.sync %0, %1;" ::"r"(1 + warp / p.sync_group), "r"(p.sync_group * 32) : "memory");
                 else __syncthreads();
             }
             // ---------------------------------------------------------------- load
             if (s == 0 || s == 2) {
                 const int frame = s >> 1;
                 stage_wait(frame);
-                if constexpr (LOADER == LD_FRAME_INT) {
+                if constexpr (LOADER == LD_FRAME_INT || LOADER == LD_FRAME_ALN) {
                     const TileDesc* desc = reinterpret_cast<const TileDesc*>(smem + S::TD_OFF);
                     const int d = desc[wi * 2 + frame].d;
                     uint32_t w0[W / 4], w1[W / 4];

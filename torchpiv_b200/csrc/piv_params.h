@@ -8,7 +8,10 @@ enum Loader : int {
     LD_FRAME_INT = 0,   // windows cut from the frame with an integer shift (pass 1, DWS)
     LD_FRAME_CWS = 1,   // windows cut with a per-window float32 shift + 2x2 bilinear taps (CWS)
     LD_EXPL_F32 = 2,    // windows already materialised as [N, w, w] float32
-    LD_EXPL_U8 = 3      // ... or uint8
+    LD_EXPL_U8 = 3,     // ... or uint8
+    LD_FRAME_ALN = 4    // LD_FRAME_INT without shifts on a grid whose step is a multiple of 16 px (the usual
+                        // first pass): every tile row starts 16-byte aligned, so the TMA box is exactly the
+                        // window and the loader needs no realignment network
 };
 
 enum Sink : int {

@@ -52,7 +52,9 @@ static int make_frame_map(CUtensorMap* map, const uint8_t* base, int n_pairs, lo
     cuuint64_t strides[2] = {static_cast<cuuint64_t>(pitch), static_cast<cuuint64_t>(ps)};
     cuuint32_t box[3] = {static_cast<cuuint32_t>(bx), static_cast<cuuint32_t>(by), 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    const CUtensorMapSwizzle swz = (bx == 32) ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    // = Tile<W, LOADER>::SWZ
+    const CUtensorMapSwizzle swz = (bx == 32) ? CU_TENSOR_MAP_SWIZZLE_32B
+                                              : ((bx == 64) ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(base), dims, strides,
                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -110,12 +112,16 @@ static int run_frame_pass(const uint8_t* fa, const uint8_t* fb, int n_pairs, lon
     p.n_total = static_cast<long long>(n_rows) * n_cols * n_pairs;
     p.div_n = make_fastdiv(static_cast<uint32_t>(n_rows) * static_cast<uint32_t>(n_cols));
     p.div_c = make_fastdiv(static_cast<uint32_t>(n_cols));
+    // unshifted windows on a grid whose step is a multiple of 16 px (the usual first pass) start 16-byte
+    // aligned in every row: the aligned loader skips the realignment network (PIVB200_NO_ALIGNED=1: A/B knob)
+    static const bool no_aligned = [] { const char* e = getenv("PIVB200_NO_ALIGNED"); return e && e[0] == '1'; }();
+    if (loader == LD_FRAME_INT && p.sxi == nullptr && p.step % 16 == 0 && !no_aligned) loader = LD_FRAME_ALN;
     CUtensorMap ta, tb;
     memset(&ta, 0, sizeof(ta));
     memset(&tb, 0, sizeof(tb));
     p.use_tma = tma_ok(fa, fb, n_pairs, pair_stride, pitch) ? 1 : 0;
     if (p.use_tma) {
-        const int bx = wind + 16;                                  // = Tile<W, LOADER>::BX
+        const int bx = (loader == LD_FRAME_ALN) ? wind : wind + 16;   // = Tile<W, LOADER>::BX
         const int by = (loader == LD_FRAME_CWS) ? wind + 1 : wind;
         if (make_frame_map(&ta, fa, n_pairs, pair_stride, H, W, pitch, bx, by) ||
             make_frame_map(&tb, fb, n_pairs, pair_stride, H, W, pitch, bx, by))
@@ -127,28 +133,52 @@ static int run_frame_pass(const uint8_t* fa, const uint8_t* fb, int n_pairs, lon
 // ----------------------------------------------------------------------------------------
 // predictor resampling: T = U * Ax^T, S = Ay * T for the fields u, v, mask (FP64)
 // ----------------------------------------------------------------------------------------
+// Both kernels give a thread RB = 4 outputs that share one operand (register blocking: 4 independent
+// FP64 accumulation chains per field and 5 instead of 8 loads per 4 FMAs); every output is still summed
+// in ascending q, so the result does not depend on the blocking.
+constexpr int kPredRB = 4;
+
 __global__ void predictor_rows_kernel(const double* __restrict__ u, const double* __restrict__ v,
                                       const uint8_t* __restrict__ mask, int n_pairs, int n0, int m0,
                                       int m1, const double* __restrict__ Ax, double* __restrict__ tmp) {
-    // tmp[f][pair][i][j] = sum_q F[pair][i][q] * Ax[j][q]
+    // tmp[f][pair][i][j] = sum_q F[pair][i][q] * Ax[j][q]; a thread owns rows i..i+3 of one (f, pair, j)
+    constexpr int RB = kPredRB;
+    const int ib = (n0 + RB - 1) / RB;
     const long long per_field = static_cast<long long>(n_pairs) * n0 * m1;
+    const long long per_field_t = static_cast<long long>(n_pairs) * ib * m1;
     const int nf = mask ? 3 : 2;
-    for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < per_field * nf;
+    for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < per_field_t * nf;
          e += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int f = static_cast<int>(e / per_field);
-        const long long r = e - f * per_field;
+        const int f = static_cast<int>(e / per_field_t);
+        long long r = e - f * per_field_t;
         const int j = static_cast<int>(r % m1);
-        const long long row = r / m1;                    // pair * n0 + i
+        r /= m1;
+        const int i0 = static_cast<int>(r % ib) * RB;
+        const long long pair = r / ib;
         const double* ax = Ax + static_cast<long long>(j) * m0;
-        double acc = 0.0;
+        double acc[RB] = {0.0, 0.0, 0.0, 0.0};
+        int row[RB];
+#pragma unroll
+        for (int k = 0; k < RB; ++k) row[k] = min(i0 + k, n0 - 1);       // clamped rows are computed but not stored
         if (f < 2) {
-            const double* src = (f == 0 ? u : v) + row * m0;
-            for (int q = 0; q < m0; ++q) acc = fma(src[q], ax[q], acc);
+            const double* src = (f == 0 ? u : v) + pair * n0 * m0;
+            for (int q = 0; q < m0; ++q) {
+                const double a = ax[q];
+#pragma unroll
+                for (int k = 0; k < RB; ++k) acc[k] = fma(src[static_cast<long long>(row[k]) * m0 + q], a, acc[k]);
+            }
         } else {
-            const uint8_t* src = mask + row * m0;
-            for (int q = 0; q < m0; ++q) acc = fma(src[q] ? 1.0 : 0.0, ax[q], acc);
+            const uint8_t* src = mask + pair * n0 * m0;
+            for (int q = 0; q < m0; ++q) {
+                const double a = ax[q];
+#pragma unroll
+                for (int k = 0; k < RB; ++k)
+                    acc[k] = fma(src[static_cast<long long>(row[k]) * m0 + q] ? 1.0 : 0.0, a, acc[k]);
+            }
         }
-        tmp[e] = acc;
+#pragma unroll
+        for (int k = 0; k < RB; ++k)
+            if (i0 + k < n0) tmp[f * per_field + (pair * n0 + i0 + k) * m1 + j] = acc[k];
     }
 }
 
@@ -158,42 +188,58 @@ __global__ void predictor_cols_kernel(const double* __restrict__ tmp, int has_ma
                                       void* __restrict__ shift_x, void* __restrict__ shift_y,
                                       double* __restrict__ base_u, double* __restrict__ base_v,
                                       double* __restrict__ pred_u, double* __restrict__ pred_v) {
+    // a thread owns output rows i..i+3 of one (pair, j): every tmp element it loads feeds 4 FMAs per field
+    constexpr int RB = kPredRB;
+    const int ib = (n1 + RB - 1) / RB;
     const long long per_field = static_cast<long long>(n_pairs) * n0 * m1;
-    const long long n_out = static_cast<long long>(n_pairs) * n1 * m1;
-    for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < n_out;
-         e += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int j = static_cast<int>(e % m1);
-        const long long r = e / m1;
-        const int i = static_cast<int>(r % n1);
-        const long long pair = r / n1;
-        const double* ay = Ay + static_cast<long long>(i) * n0;
+    const long long n_thr = static_cast<long long>(n_pairs) * ib * m1;
+    for (long long t_id = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t_id < n_thr;
+         t_id += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int j = static_cast<int>(t_id % m1);
+        const long long r = t_id / m1;
+        const int i0 = static_cast<int>(r % ib) * RB;
+        const long long pair = r / ib;
         const double* t = tmp + (pair * n0) * m1 + j;
-        double su = 0.0, sv = 0.0, sm = 0.0;
+        const double* ay[RB];
+#pragma unroll
+        for (int k = 0; k < RB; ++k) ay[k] = Ay + static_cast<long long>(min(i0 + k, n1 - 1)) * n0;
+        double su[RB] = {0.0, 0.0, 0.0, 0.0}, sv[RB] = {0.0, 0.0, 0.0, 0.0}, sm[RB] = {0.0, 0.0, 0.0, 0.0};
         for (int q = 0; q < n0; ++q) {
-            const double a = ay[q];
-            su = fma(a, t[static_cast<long long>(q) * m1], su);
-            sv = fma(a, t[per_field + static_cast<long long>(q) * m1], sv);
-            if (has_mask) sm = fma(a, t[2 * per_field + static_cast<long long>(q) * m1], sm);
+            const double tu = t[static_cast<long long>(q) * m1];
+            const double tv = t[per_field + static_cast<long long>(q) * m1];
+            const double tm = has_mask ? t[2 * per_field + static_cast<long long>(q) * m1] : 0.0;
+#pragma unroll
+            for (int k = 0; k < RB; ++k) {
+                const double a = ay[k][q];
+                su[k] = fma(a, tu, su[k]);
+                sv[k] = fma(a, tv, sv[k]);
+                if (has_mask) sm[k] = fma(a, tm, sm[k]);
+            }
         }
-        const bool inval = has_mask && (sm >= 0.5);           // PB:711 / 778
-        const double pu = inval ? 0.0 : su, pv = inval ? 0.0 : sv;
-        pred_u[e] = pu;
-        pred_v[e] = pv;
-        if (MODE == PIVB200_MODE_CWS) {
-            // PB:705-706: halves taken BEFORE the invalid zeroing; shift = float32(u0 / 2)
-            const double hu = su / 2, hv = sv / 2;
-            static_cast<float*>(shift_x)[e] = static_cast<float>(hu);
-            static_cast<float*>(shift_y)[e] = static_cast<float>(hv);
-            base_u[e] = 2 * hu;
-            base_v[e] = 2 * hv;
-        } else {
-            // PB:782-790: zeroing first, round-half-even
-            const double ru = rint(pu / 2), rv = rint(pv / 2);
-            const double lim = 1048576.0;
-            static_cast<int*>(shift_x)[e] = static_cast<int>(fmin(fmax(ru, -lim), lim));
-            static_cast<int*>(shift_y)[e] = static_cast<int>(fmin(fmax(rv, -lim), lim));
-            base_u[e] = 2 * ru;
-            base_v[e] = 2 * rv;
+#pragma unroll
+        for (int k = 0; k < RB; ++k) {
+            if (i0 + k >= n1) break;
+            const long long e = (pair * n1 + i0 + k) * m1 + j;
+            const bool inval = has_mask && (sm[k] >= 0.5);           // PB:711 / 778
+            const double pu = inval ? 0.0 : su[k], pv = inval ? 0.0 : sv[k];
+            pred_u[e] = pu;
+            pred_v[e] = pv;
+            if (MODE == PIVB200_MODE_CWS) {
+                // PB:705-706: halves taken BEFORE the invalid zeroing; shift = float32(u0 / 2)
+                const double hu = su[k] / 2, hv = sv[k] / 2;
+                static_cast<float*>(shift_x)[e] = static_cast<float>(hu);
+                static_cast<float*>(shift_y)[e] = static_cast<float>(hv);
+                base_u[e] = 2 * hu;
+                base_v[e] = 2 * hv;
+            } else {
+                // PB:782-790: zeroing first, round-half-even
+                const double ru = rint(pu / 2), rv = rint(pv / 2);
+                const double lim = 1048576.0;
+                static_cast<int*>(shift_x)[e] = static_cast<int>(fmin(fmax(ru, -lim), lim));
+                static_cast<int*>(shift_y)[e] = static_cast<int>(fmin(fmax(rv, -lim), lim));
+                base_u[e] = 2 * ru;
+                base_v[e] = 2 * rv;
+            }
         }
     }
 }
@@ -543,11 +589,11 @@ int pivb200_predictor(const double* u_prev, const double* v_prev, const uint8_t*
     if (mode != PIVB200_MODE_CWS && mode != PIVB200_MODE_DWS) return PIVB200_E_ARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int nf = mask_prev ? 3 : 2;
-    const long long n_tmp = static_cast<long long>(n_pairs) * n0 * m1 * nf;
+    const long long n_tmp = static_cast<long long>(n_pairs) * ((n0 + kPredRB - 1) / kPredRB) * m1 * nf;
     predictor_rows_kernel<<<grid_for(n_tmp, 128), 128, 0, s>>>(u_prev, v_prev, mask_prev, n_pairs, n0, m0,
                                                                m1, Ax, tmp);
     count_launch();
-    const long long n_out = static_cast<long long>(n_pairs) * n1 * m1;
+    const long long n_out = static_cast<long long>(n_pairs) * ((n1 + kPredRB - 1) / kPredRB) * m1;
     if (mode == PIVB200_MODE_CWS)
         predictor_cols_kernel<PIVB200_MODE_CWS><<<grid_for(n_out, 128), 128, 0, s>>>(
             tmp, mask_prev != nullptr, n_pairs, n0, n1, m1, Ay, shift_x, shift_y, base_u, base_v, pred_u, pred_v);
