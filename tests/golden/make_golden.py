@@ -215,8 +215,46 @@ def gen_output_formats():
         shutil.rmtree(tmp)
 
 
+def gen_general_sizes():
+    """Window sizes outside 16/32/64 (general direct-DFT kernel): first passes, a 64 -> 42 -> 28 chain
+    (what multipass_scale = 1.5 produces, PB:855-857) at the function boundary, and the generator."""
+    out = {}
+    a, b = cases.small_pair(seed=3, kind="vortex", zero_patch=True)
+    ta, tb = torch.tensor(a), torch.tensor(b)
+    out["sha"] = np.array(cases.sha(a, b))
+    for w, o in cases.GENERAL_GEOMS:
+        u, v, x, y, m = PB.extended_search_area_piv(ta, tb, window_size=w, overlap=o, validate=True)
+        out[f"p1_{w}_{o}_u"], out[f"p1_{w}_{o}_v"], out[f"p1_{w}_{o}_mask"] = u, v, m
+        out[f"p1_{w}_{o}_x"], out[f"p1_{w}_{o}_y"] = x, y
+    for mode in ("CWS", "DWS"):
+        u, v, x, y, m = PB.extended_search_area_piv(ta, tb, window_size=64, overlap=32, validate=True)
+        out[f"{mode}_p0_u"], out[f"{mode}_p0_v"], out[f"{mode}_p0_mask"] = u, v, m
+        w, o = 64, 32
+        for it in (1, 2):
+            w, o = int(w // 1.5), int(o // 1.5)
+            fn = PB.IterModMap.functions[mode](ta.shape, w, o, CPU)
+            u, v, x, y, m = quiet(fn, ta, tb, x, y, u.copy(), v.copy(), m.copy())
+            out[f"{mode}_p{it}_u"], out[f"{mode}_p{it}_v"], out[f"{mode}_p{it}_mask"] = u, v, m
+            out[f"{mode}_p{it}_x"], out[f"{mode}_p{it}_y"] = x, y
+    tmp = tempfile.mkdtemp(prefix="pivgold_")
+    try:
+        pairs = [cases.small_pair(seed=10 + i, kind="uniform" if i % 2 == 0 else "vortex") for i in range(2)]
+        synth.write_pair_folder(tmp, pairs)
+        gen = PB.OfflinePIV(folder=tmp, device="cpu", file_fmt="bmp", wind_size=64, overlap=32, multipass=2,
+                            multipass_mode="CWS", multipass_scale=1.5, dt=12, scale=0.02, folder_mode="pairs")
+        res = quiet(lambda: list(gen()))
+        out["offline_n"] = np.array([len(gen), len(res)])
+        for i, (x, y, u, v) in enumerate(res):
+            out[f"offline_{i}_x"], out[f"offline_{i}_y"] = x, y
+            out[f"offline_{i}_u"], out[f"offline_{i}_v"] = u, v
+    finally:
+        shutil.rmtree(tmp)
+    save("general_sizes.npz", **out)
+
+
 GENERATORS = {"pass1": gen_pass1, "multipass": gen_multipass, "shift": gen_shift, "corr2disp": gen_corr2disp,
-              "offline": gen_offline, "statistics": gen_statistics, "output_formats": gen_output_formats}
+              "offline": gen_offline, "statistics": gen_statistics, "output_formats": gen_output_formats,
+              "general_sizes": gen_general_sizes}
 
 if __name__ == "__main__":
     # no arguments: regenerate everything; otherwise only the named fixtures

@@ -81,10 +81,10 @@ def conditioning(corr, val_ratio=1.2, rel=1e-6):
     return (sens < COND_PX) & ~tie & ~border
 
 
-def check_field(got_u, got_v, got_m, ref_u, ref_v, ref_m, corr, tight=2e-5):
+def check_field(got_u, got_v, got_m, ref_u, ref_v, ref_m, corr, tight=2e-5, max_ill=MAX_ILL):
     """got = CUDA path, ref = reference (golden / oracle), corr = the oracle's maps (conditioning)."""
     well = conditioning(corr).reshape(ref_u.shape)
-    assert 1.0 - well.mean() <= MAX_ILL, f"too many ill-conditioned vectors: {1 - well.mean():.3f}"
+    assert 1.0 - well.mean() <= max_ill, f"too many ill-conditioned vectors: {1 - well.mean():.3f}"
     if ref_m is not None:
         assert (~well & ~ref_m).sum() <= MAX_ILL_VALID * max(1, (~ref_m).sum())
         assert np.array_equal(got_m[well], ref_m[well]), "validation mask differs on well-conditioned vectors"
@@ -250,7 +250,7 @@ def test_pass_first_api(T, golden):
     with pytest.raises(ValueError):
         T.extended_search_area_piv(fa, fb, window_size=512, overlap=0)
     with pytest.raises(ValueError):
-        T.extended_search_area_piv(fa, fb, window_size=48, overlap=24)     # no FFT kernel: fails loudly
+        T.extended_search_area_piv(fa, fb, window_size=33, overlap=11)     # odd window: fails loudly
 
 
 @pytest.mark.parametrize("mode", ["CWS", "DWS"])
@@ -438,9 +438,11 @@ def test_error_codes_through_c_abi(G):
     mk = torch.zeros(16, dtype=torch.uint8, device="cuda")
     args = lambda w, ov: (t.data_ptr(), t.data_ptr(), 1, 0, 64, 64, 64, w, ov, 1, 1.2, o.data_ptr(),  # noqa: E731
                           o.data_ptr(), mk.data_ptr(), None, None)
-    assert L.pivb200_pass_first(*args(48, 24)) == _lib.E_WINDOW
+    assert L.pivb200_pass_first(*args(47, 24)) == _lib.E_WINDOW
     assert L.pivb200_pass_first(*args(32, 32)) == _lib.E_OVERLAP
-    assert L.pivb200_pass_first(*args(128, 0)) == _lib.E_WINDOW
+    assert L.pivb200_pass_first(*args(48, 48)) == _lib.E_OVERLAP
+    assert L.pivb200_pass_first(*args(128, 0)) == _lib.E_FRAME
+    assert L.pivb200_pass_first(*args(130, 0)) == _lib.E_WINDOW
     assert L.pivb200_pass_first(*args(64, 0)) == 0
     bad = list(args(32, 16)); bad[11] = None
     assert L.pivb200_pass_first(*bad) == _lib.E_ARG

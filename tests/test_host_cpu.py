@@ -51,8 +51,12 @@ def test_error_strings_and_geometry_checks_without_gpu():
     assert "larger than the image" in _lib.error_string(_lib.E_FRAME)
     # argument validation happens before any CUDA call, so it is testable here
     dummy = ctypes.c_void_p(0x1000)
-    rc = L.pivb200_pass_first(dummy, dummy, 1, 0, 64, 64, 64, 48, 24, 1, 1.2, dummy, dummy, dummy, None, None)
-    assert rc == _lib.E_WINDOW
+    for bad_window in (47, 130, 2):      # odd / above 128 / below 4 (48 would take the general kernel)
+        rc = L.pivb200_pass_first(dummy, dummy, 1, 0, 256, 256, 256, bad_window, 0, 1, 1.2, dummy, dummy, dummy,
+                                  None, None)
+        assert rc == _lib.E_WINDOW
+    rc = L.pivb200_pass_first(dummy, dummy, 1, 0, 64, 64, 64, 48, 50, 1, 1.2, dummy, dummy, dummy, None, None)
+    assert rc == _lib.E_OVERLAP
     rc = L.pivb200_pass_first(dummy, dummy, 1, 0, 64, 64, 64, 32, 40, 1, 1.2, dummy, dummy, dummy, None, None)
     assert rc == _lib.E_OVERLAP
     rc = L.pivb200_pass_first(dummy, dummy, 1, 0, 16, 16, 16, 32, 16, 1, 1.2, dummy, dummy, dummy, None, None)

@@ -151,3 +151,35 @@ def test_offline_pipeline(golden, tag, kw):
         dv = np.abs(v - g[f"{tag}_{i}_v"]) / k
         assert np.quantile(du, 0.99) < 1e-4 and np.quantile(dv, 0.99) < 1e-4
         assert du.max() < 5e-2 and dv.max() < 5e-2   # chained float32 passes near invalid vectors
+
+
+@pytest.mark.parametrize("w,o", cases.GENERAL_GEOMS)
+def test_pass1_general_window_sizes(golden, w, o):
+    """Windows that are not 16/32/64 px (the general kernel's oracle)."""
+    g = golden("general_sizes.npz")
+    a, b = cases.small_pair(seed=3, kind="vortex", zero_patch=True)
+    assert cases.sha(a, b) == str(g["sha"])
+    u, v, x, y, m = O.extended_search_area_piv(a, b, w, o, validate=True)
+    assert np.array_equal(m, g[f"p1_{w}_{o}_mask"])
+    assert np.array_equal(x, g[f"p1_{w}_{o}_x"]) and np.array_equal(y, g[f"p1_{w}_{o}_y"])
+    assert np.abs(u - g[f"p1_{w}_{o}_u"]).max() < TOL64 and np.abs(v - g[f"p1_{w}_{o}_v"]).max() < TOL64
+
+
+@pytest.mark.parametrize("mode", ["CWS", "DWS"])
+def test_multipass_scale_1p5_function_boundary(golden, mode):
+    """64 -> 42 -> 28 px (multipass_scale = 1.5), each pass fed the reference's previous output."""
+    g = golden("general_sizes.npz")
+    a, b = cases.small_pair(seed=3, kind="vortex", zero_patch=True)
+    x, y = O.get_coordinates(a.shape, 64, 32)
+    w, o = 64, 32
+    for it in (1, 2):
+        u0, v0, m0 = (g[f"{mode}_p{it-1}_{k}"].copy() for k in ("u", "v", "mask"))
+        w, o = int(w // 1.5), int(o // 1.5)
+        fn = O.ITER_MODES[mode](a.shape, w, o)
+        u, v, x1, y1, m = fn(a, b, x, y, u0, v0, m0)
+        assert np.array_equal(x1, g[f"{mode}_p{it}_x"]) and np.array_equal(y1, g[f"{mode}_p{it}_y"])
+        assert (m != g[f"{mode}_p{it}_mask"]).mean() <= 0.01
+        for got, key in ((u, "u"), (v, "v")):
+            err = np.abs(got - g[f"{mode}_p{it}_{key}"])
+            assert np.quantile(err, 0.98) < TOL32 and np.quantile(err, 0.995) < 1e-3
+        x, y = x1, y1

@@ -93,9 +93,17 @@ static int launch_fused(int wind, int loader, int sink, const CUtensorMap& ta, c
     return PIVB200_E_WINDOW;
 }
 
+// general window sizes (generic_pass.cuh, included further down)
+static int run_generic(const uint8_t* fa, const uint8_t* fb, int n_pairs, long long pair_stride, int H, int W,
+                       int pitch, int wind, int overlap, int loader, int sink, const PassParams& p,
+                       cudaStream_t stream);
+static inline bool fused_window(int wind) { return wind == 16 || wind == 32 || wind == 64; }
+
 static int run_frame_pass(const uint8_t* fa, const uint8_t* fb, int n_pairs, long long pair_stride,
                           int H, int W, int pitch, int wind, int overlap, int loader, int sink,
                           PassParams& p, cudaStream_t stream) {
+    if (!fused_window(wind))
+        return run_generic(fa, fb, n_pairs, pair_stride, H, W, pitch, wind, overlap, loader, sink, p, stream);
     int n_rows, n_cols;
     int rc = check_geometry(H, W, pitch, wind, overlap, n_pairs, &n_rows, &n_cols);
     if (rc) return rc;
@@ -438,6 +446,40 @@ static int grid_for(long long n, int block) {
 }
 
 }  // namespace pivb200
+#include "generic_pass.cuh"
+namespace pivb200 {
+
+static int run_generic(const uint8_t* fa, const uint8_t* fb, int n_pairs, long long pair_stride, int H, int W,
+                       int pitch, int wind, int overlap, int loader, int sink, const PassParams& p,
+                       cudaStream_t stream) {
+    const int mode = (loader == LD_FRAME_CWS) ? PIVB200_MODE_CWS : PIVB200_MODE_DWS;
+    if (sink == SK_DISP)
+        return run_generic_pass(fa, fb, n_pairs, pair_stride, H, W, pitch, wind, overlap, p, mode, stream);
+    if (sink != SK_WIN) return PIVB200_E_ARG;
+    // the (shifted) windows only
+    if (!generic_window_ok(wind)) return PIVB200_E_WINDOW;
+    if (overlap >= wind || overlap < 0) return PIVB200_E_OVERLAP;
+    if (wind > H || wind > W || pitch < W) return PIVB200_E_FRAME;
+    if (!fa || !fb || n_pairs < 1) return PIVB200_E_ARG;
+    GenericParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.fa = fa; gp.fb = fb;
+    gp.pair_stride = (n_pairs > 1) ? pair_stride : static_cast<long long>(H) * pitch;
+    gp.H = H; gp.Wf = W; gp.pitch = pitch;
+    gp.wind = wind;
+    gp.n_rows = (H - wind) / (wind - overlap) + 1;
+    gp.n_cols = (W - wind) / (wind - overlap) + 1;
+    gp.step = wind - overlap;
+    gp.mode = mode;
+    gp.sxf = p.sxf; gp.syf = p.syf; gp.sxi = p.sxi; gp.syi = p.syi;
+    gp.n_windows = static_cast<long long>(gp.n_rows) * gp.n_cols * n_pairs;
+    if (gp.n_windows >= (1ll << 30) || static_cast<long long>(H) * W >= (1ll << 31)) return PIVB200_E_SIZE;
+    gp.win_a_out = p.win_a_out;
+    gp.win_b_out = p.win_b_out;
+    return generic_launch(gp, stream);
+}
+
+}  // namespace pivb200
 
 using namespace pivb200;
 
@@ -451,7 +493,7 @@ int pivb200_version(void) { return 100; }
 const char* pivb200_error_string(int code) {
     switch (code) {
         case PIVB200_OK: return "ok";
-        case PIVB200_E_WINDOW: return "interrogation window must be 16, 32 or 64 px";
+        case PIVB200_E_WINDOW: return "interrogation window must be an even size of 4..128 px (16/32/64 px: fused kernels)";
         case PIVB200_E_OVERLAP: return "Overlap has to be smaller than the window_size";
         case PIVB200_E_FRAME: return "window size cannot be larger than the image";
         case PIVB200_E_ARG: return "invalid argument (null or misaligned pointer, bad count)";
@@ -556,11 +598,22 @@ int pivb200_windows(const uint8_t* frames_a, const uint8_t* frames_b, int n_pair
 
 int pivb200_correlate(const void* windows_a, const void* windows_b, int dtype, long long n,
                       int wind, float* corr, void* stream) {
-    if (wind != 16 && wind != 32 && wind != 64) return PIVB200_E_WINDOW;
+    if (!fused_window(wind) && !generic_window_ok(wind)) return PIVB200_E_WINDOW;
     if (!windows_a || !windows_b || !corr || n < 1 || (dtype != 0 && dtype != 1)) return PIVB200_E_ARG;
     if ((reinterpret_cast<uintptr_t>(windows_a) | reinterpret_cast<uintptr_t>(windows_b)) & 15)
         return PIVB200_E_ARG;
     if (n >= (1ll << 30)) return PIVB200_E_SIZE;
+    if (!fused_window(wind)) {
+        GenericParams gp;
+        memset(&gp, 0, sizeof(gp));
+        gp.wind = wind;
+        gp.n_windows = n;
+        gp.wa = windows_a;
+        gp.wb = windows_b;
+        gp.explicit_dtype = dtype;
+        gp.corr_out = corr;
+        return generic_launch(gp, static_cast<cudaStream_t>(stream));
+    }
     PassParams p;
     memset(&p, 0, sizeof(p));
     p.wa = windows_a;

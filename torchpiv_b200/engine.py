@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .geometry import SUPPORTED_WINDOWS, get_coordinates, get_field_shape, spline_operator
+from .geometry import MAX_WINDOW, get_coordinates, get_field_shape, spline_operator, window_supported
 
 __all__ = ["PassGeometry", "PIVPlan", "pass_schedule", "HostPipeline", "FramePipeline"]
 
@@ -52,10 +52,11 @@ def _geometry(frame_shape, wind, overlap) -> PassGeometry:
         raise ValueError("Overlap has to be smaller than the window_size")
     if wind > frame_shape[-2] or wind > frame_shape[-1]:
         raise ValueError("window size cannot be larger than the image")
-    if wind not in SUPPORTED_WINDOWS:
-        raise ValueError(f"interrogation window must be one of {SUPPORTED_WINDOWS} px "
-                         f"(got {wind}); the sm_100a kernels use in-register radix-8/4 FFTs "
-                         "and there is no fallback path")
+    if not window_supported(wind):
+        raise ValueError(f"interrogation window must be an even size of 4..{MAX_WINDOW} px (got {wind}): "
+                         "16/32/64 px run the fused in-register FFT kernels, other even sizes the "
+                         "general direct-DFT kernel; odd sizes are not supported (the reference's "
+                         "irfft2 returns a [w, w-1] map for them) and there is no CPU fallback")
     n_rows, n_cols = (int(v) for v in get_field_shape(frame_shape, wind, overlap)[-2:])
     x, y = get_coordinates(frame_shape, wind, overlap)
     return PassGeometry(wind, overlap, n_rows, n_cols, x, y)
