@@ -224,3 +224,44 @@ def test_synthetic_images_are_deterministic():
     a2, b2 = cases.small_pair(seed=3)
     assert np.array_equal(a1, a2) and np.array_equal(b1, b2)
     assert a1.dtype == np.uint8 and 5 < a1.mean() < 60
+
+
+def test_read_gray_into_fast_bmp_path_equals_opencv(tmp_path):
+    """Uncompressed 8-bit grey-palette BMPs are copied straight out of the file; everything else goes
+    through OpenCV.  Both must give what the reference's decode (cv2.imdecode GRAYSCALE, PB:136-137) gives."""
+    import cv2
+    from torchpiv_b200 import dataset, synth
+    rng = np.random.default_rng(0)
+    for shape in ((37, 53), (64, 62), (128, 256)):
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        files = {}
+        files["synth"] = str(tmp_path / f"s{shape[1]}.bmp")
+        synth.write_bmp(files["synth"], img)
+        files["cv2"] = str(tmp_path / f"c{shape[1]}.bmp")
+        cv2.imwrite(files["cv2"], img)
+        files["png"] = str(tmp_path / f"p{shape[1]}.png")
+        cv2.imwrite(files["png"], img)
+        for kind, path in files.items():
+            raw = np.fromfile(path, dtype=np.uint8)
+            assert (dataset._bmp8_view(raw) is not None) == (kind != "png"), kind
+            dst = np.full(shape, 7, dtype=np.uint8)
+            assert dataset.read_gray_into(path, dst)
+            assert np.array_equal(dst, cv2.imdecode(raw, cv2.IMREAD_GRAYSCALE)) and np.array_equal(dst, img)
+    # colour BMP: not the fast format, OpenCV converts
+    col = rng.integers(0, 256, (20, 24, 3), dtype=np.uint8)
+    path = str(tmp_path / "col.bmp")
+    cv2.imwrite(path, col)
+    raw = np.fromfile(path, dtype=np.uint8)
+    assert dataset._bmp8_view(raw) is None
+    dst = np.empty((20, 24), dtype=np.uint8)
+    assert dataset.read_gray_into(path, dst) and np.array_equal(dst, cv2.imdecode(raw, cv2.IMREAD_GRAYSCALE))
+    # a grey BMP whose palette is NOT the identity ramp must not take the fast path
+    raw = np.fromfile(files["synth"], dtype=np.uint8).copy()
+    raw[54 + 4 * 10] = 200
+    assert dataset._bmp8_view(raw) is None
+    # truncated / missing / wrong shape
+    trunc = str(tmp_path / "t.bmp")
+    open(trunc, "wb").write(np.fromfile(files["synth"], dtype=np.uint8)[:2000].tobytes())
+    assert not dataset.read_gray_into(trunc, np.empty((128, 256), dtype=np.uint8))
+    assert not dataset.read_gray_into(str(tmp_path / "missing.bmp"), dst)
+    assert not dataset.read_gray_into(files["synth"], np.empty((5, 5), dtype=np.uint8))

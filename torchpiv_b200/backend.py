@@ -24,7 +24,7 @@ import torch
 
 from . import _lib
 from .dataset import (PIVDataset, ToTensor, natural_keys, plan_batches, read_gray,  # noqa: F401
-                      shard_range)
+                      read_gray_into, shard_range)
 from .engine import PIVPlan, pass_schedule
 from .geometry import get_coordinates, get_field_shape, spline_operator  # noqa: F401
 from .postprocess import finalize_field
@@ -369,16 +369,9 @@ class OfflinePIV:
     # -- decoding ------------------------------------------------------------------------------
     def _decode_into(self, path: str, dst: np.ndarray) -> bool:
         """Decode one frame straight into pinned staging memory; False = unreadable / wrong shape."""
-        img = read_gray(path)
-        if img is None:
-            return False
         if self._plan is None:
             return False
-        if img.shape != dst.shape:
-            print(f"Warning! {path}: frame shape {img.shape} != {dst.shape}, pair skipped")
-            return False
-        np.copyto(dst, img)
-        return True
+        return read_gray_into(path, dst)
 
     def _ensure_plan(self, batches) -> bool:
         """The constructor could not read the first frame: find the first readable one."""
@@ -422,13 +415,14 @@ class OfflinePIV:
                         for j, path in enumerate(batches[n].files)]
 
             def finish(n, ok):
-                """Results of batch n -> finished fields of its readable pairs, in order."""
+                """Results of batch n -> finished fields of its readable pairs, in order.  The per-pair host
+                post-processing (SciPy Delaunay fill in the reference mode) runs on the worker pool too."""
                 u, v, bad = pipe.result(n & 1)
                 batch = batches[n]
-                for i in range(len(batch)):
-                    if not (ok[batch.index_a[i]] and ok[batch.index_b[i]]):
-                        continue
-                    out = self._finalize(u[i].copy(), v[i].copy(), geo, bad[i])
+                jobs = [pool.submit(self._finalize, u[i].copy(), v[i].copy(), geo, bad[i])
+                        for i in range(len(batch)) if ok[batch.index_a[i]] and ok[batch.index_b[i]]]
+                for job in jobs:
+                    out = job.result()
                     if out is not None:
                         yield out
 
