@@ -393,6 +393,41 @@ def test_full_size_against_oracle(T, big_pair):
     assert eu.max() < 5e-2 and ev.max() < 5e-2
 
 
+def test_full_size_vortex_three_pass(T):
+    """BASELINE config 4: 4 MP Rankine vortex (core radius 256 px, peak 6 px), 3-pass CWS 64 -> 32 -> 16 px.
+    The recovered field follows the imposed one at the window centres."""
+    from torchpiv_b200 import synth
+    shape = (2048, 2048)
+    field = synth.rankine_vortex(1024, 1024, 256, 6.0)
+    a, b = synth.particle_pair(shape, field, seed=4)
+    plan = T.PIVPlan(shape, 64, 32, 3, "CWS", 2.0, device="cuda:0")
+    u, v, m = (t[0].cpu().numpy() for t in plan.run(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()))
+    g = plan.out_geometry
+    assert u.shape == (255, 255)
+    ok = ~m.astype(bool)
+    assert ok.mean() > 0.9
+    # particles at p move to p + d(p): the window centred at c sees the displacement imposed around c - d/2
+    du, dv = field(g.x, g.y)
+    du, dv = field(g.x - du / 2, g.y - dv / 2)
+    eu, ev = np.abs(u - du)[ok], np.abs(v - dv)[ok]
+    assert np.median(eu) < 0.08 and np.median(ev) < 0.08
+    assert np.quantile(eu, 0.95) < 0.5 and np.quantile(ev, 0.95) < 0.5
+    assert np.hypot(u[ok], v[ok]).max() < 8.0 and np.hypot(u[ok], v[ok]).max() > 5.0
+
+
+def test_full_size_dws_against_oracle(T, big_pair):
+    """BASELINE config 3: one 4 MP 2-pass DWS pair vs the oracle."""
+    a, b = big_pair
+    plan = T.PIVPlan(a.shape, 64, 32, 2, "DWS", 2.0, device="cuda:0")
+    u, v, m = (t[0].cpu().numpy() for t in plan.run(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()))
+    ou, ov, _, _, om, _ = O.piv_passes(a, b, 64, 32, 2, "DWS")
+    assert (m.astype(bool) != om).mean() < 2e-3
+    ok = ~om & ~m.astype(bool)
+    eu, ev = np.abs(u - ou)[ok], np.abs(v - ov)[ok]
+    assert np.quantile(eu, 0.999) < 1e-4 and np.quantile(ev, 0.999) < 1e-4
+    assert eu.max() < 5e-2 and ev.max() < 5e-2
+
+
 # ------------------------------------------------------------------------------------------
 # edge cases
 # ------------------------------------------------------------------------------------------
