@@ -88,6 +88,21 @@ __host__ __device__ __forceinline__ float2 cscale(float2 a, float s) {
     return make_float2(a.x * s, a.y * s);
 #endif
 }
+// element-wise a * b and a * b + c on pairs (FMUL2 / FFMA2); NOT complex products
+__host__ __device__ __forceinline__ float2 cmul2(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+    return __fmul2_rn(a, b);
+#else
+    return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+__host__ __device__ __forceinline__ float2 cfma(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+    return __ffma2_rn(a, b, c);
+#else
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
 // -i (a - b), computed directly as the rotated pair (two scalar subtractions)
 __host__ __device__ __forceinline__ float2 csub_mi(float2 a, float2 b) { return make_float2(a.y - b.y, b.x - a.x); }
 

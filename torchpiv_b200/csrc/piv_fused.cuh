@@ -123,8 +123,8 @@ struct Smem {
     using G = Geo<W>;
     using T = Tile<W, LOADER>;
     static constexpr int REG_OFF = 0;                                        // NW window buffers
-    static constexpr int XW_OFF = REG_OFF + G::NW * G::REGION;               // float2 [NW][W]  (CWS column taps)
-    static constexpr int XW = (LOADER == LD_FRAME_CWS) ? G::NW * W * 8 : 0;
+    static constexpr int XW_OFF = REG_OFF + G::NW * G::REGION;               // float4 [NW][W]  (CWS column taps, each weight twice)
+    static constexpr int XW = (LOADER == LD_FRAME_CWS) ? G::NW * W * 16 : 0;
     static constexpr int XF_OFF = XW_OFF + XW;                               // int    [NW][W]
     static constexpr int XF = (LOADER == LD_FRAME_CWS) ? G::NW * W * 4 : 0;
     static constexpr int TD_OFF = ((XF_OFF + XF + 15) / 16) * 16;            // TileDesc [NW][2]
@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                     });
                 } else if constexpr (LOADER == LD_FRAME_CWS) {
                     const TileDesc* desc = reinterpret_cast<const TileDesc*>(smem + S::TD_OFF);
-                    float2* xw = reinterpret_cast<float2*>(smem + S::XW_OFF);
+                    float4* xw = reinterpret_cast<float4*>(smem + S::XW_OFF);
                     int* xf = reinterpret_cast<int*>(smem + S::XF_OFF);
                     // per-column tap descriptors of this frame (shared by all rows of a window)
                     bool flag = false;
@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                         const int j = e & (W - 1), w2 = e >> LOGW;
                         const TileDesc dsc = desc[w2 * 2 + frame];
                         const AxisTap cx = cws_axis(dsc.c0 + j, dsc.vx);
-                        xw[e] = make_float2(cx.w1, cx.w0);
+                        xw[e] = make_float4(cx.w1, cx.w1, cx.w0, cx.w0);      // pairs: operands of the packed taps
                         xf[e] = (cx.exact ? 2 : 0) | ((cx.lo - (dsc.ox + j)) & 1);
                         flag |= cx.exact;
                         // rows: every row index appears as some j (square windows) -> same loop covers them
@@ -603,13 +603,15 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                     const bool anyflag = __any_sync(FULL, flag);
                     __syncwarp();
                     const TileDesc dsc = desc[wi * 2 + frame];
-                    const float2* xwq = xw + wi * W;
+                    const float4* xwq = xw + wi * W;
                     const int* xfq = xf + wi * W;
                     // Window rows (2l, 2l+1) need tile rows 2l .. 2l+2.  The reference's four-term sum
-                    // (PB:187-192) is evaluated in its separable form: a horizontal tap h = Q(x) wx1 +
-                    // Q(x+1) wx0 per tile row, shared by the two window rows, then the vertical tap --
-                    // same value up to FP32 rounding (~1e-7 relative; the function-level entry point
-                    // pivb200_bilinear_cws keeps the reference's exact evaluation order).
+                    // (PB:187-192) is evaluated in a separable form, vertical tap first: per tile column one
+                    // packed pair v = (A wyA1 + B wyA0, B wyB1 + C wyB0) for the lane's two window rows (A, B, C =
+                    // its three tile rows), then the horizontal tap v[j] wx1 + v[j+1] wx0, again packed -- the
+                    // result IS the FFT operand (row 2l, row 2l+1).  Same value up to FP32 rounding (~1e-7
+                    // relative; the function-level entry point pivb200_bilinear_cws keeps the reference's exact
+                    // evaluation order).  5 packed FP32 instructions per output pair instead of 10 scalar ones.
                     const int ra = 2 * l;
                     const AxisTap cyA = cws_axis(dsc.r0 + ra, dsc.vy), cyB = cws_axis(dsc.r0 + ra + 1, dsc.vy);
                     uint32_t wA[W / 4 + 1], wB[W / 4 + 1], wC[W / 4 + 1];
@@ -618,17 +620,17 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                     load_row_words<W, LOADER, W / 4 + 1>(region, ra + 2, dsc.d, wC);
                     float cA = u8f(wA[0], 0), cB = u8f(wB[0], 0), cC = u8f(wC[0], 0);
                     if (!anyflag) {
+                        const float2 wy1 = make_float2(cyA.w1, cyB.w1), wy0 = make_float2(cyA.w0, cyB.w0);
+                        float2 vc = cfma(make_float2(cA, cB), wy1, cmul2(make_float2(cB, cC), wy0));
                         static_for<0, W>([&](auto jc) {
                             constexpr int j = decltype(jc)::value;
                             const float nA = u8f(wA[(j + 1) >> 2], (j + 1) & 3);
                             const float nB = u8f(wB[(j + 1) >> 2], (j + 1) & 3);
                             const float nC = u8f(wC[(j + 1) >> 2], (j + 1) & 3);
-                            const float2 wx = xwq[j];
-                            const float hA = fmaf(cA, wx.x, nA * wx.y);
-                            const float hB = fmaf(cB, wx.x, nB * wx.y);
-                            const float hC = fmaf(cC, wx.x, nC * wx.y);
-                            x[j] = make_float2(fmaf(hA, cyA.w1, hB * cyA.w0), fmaf(hB, cyB.w1, hC * cyB.w0));
-                            cA = nA; cB = nB; cC = nC;
+                            const float2 vn = cfma(make_float2(nA, nB), wy1, cmul2(make_float2(nB, nC), wy0));
+                            const float4 wx = xwq[j];
+                            x[j] = cfma(vc, make_float2(wx.x, wx.y), cmul2(vn, make_float2(wx.z, wx.w)));
+                            vc = vn;
                         });
                     } else {
                         // some coordinate of the job is an exact integer: there the reference's weights all
@@ -639,7 +641,8 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                             const float nA = u8f(wA[(j + 1) >> 2], (j + 1) & 3);
                             const float nB = u8f(wB[(j + 1) >> 2], (j + 1) & 3);
                             const float nC = u8f(wC[(j + 1) >> 2], (j + 1) & 3);
-                            const float2 wx = xwq[j];
+                            const float4 wx4 = xwq[j];
+                            const float2 wx = make_float2(wx4.x, wx4.z);
                             const int fl = xfq[j];
                             const float hA = fmaf(cA, wx.x, nA * wx.y);
                             const float hB = fmaf(cB, wx.x, nB * wx.y);

@@ -162,7 +162,13 @@ class PIVPlan:
         return w["u"][:n_pairs], w["v"][:n_pairs], w["mask"][:n_pairs]
 
     @property
-    def launches_per_batch(self) -> int:
+    def launches_per_batch(self):
+        """Kernel launches per ``run`` when every pass takes the fused kernels (16/32/64 px windows): one
+        per pass plus two predictor kernels between passes.  None when a pass takes the general-size path,
+        whose launch count depends on the batch size (chunked scratch buffer)."""
+        from .geometry import FUSED_WINDOWS
+        if any(g.wind not in FUSED_WINDOWS for g in self.passes):
+            return None
         return 1 + 3 * (len(self.passes) - 1)
 
     @property
