@@ -15,6 +15,8 @@ one batch of PAIRS_PER_STEP synthetic 2048x2048 particle-image pairs per GPU.
   roofline     : dominant kernel (CWS pass at 32 px) against the FFMA peak measured in this run.
   cpu_baseline : the CPU oracle (NumPy/SciPy port of the reference path, all host threads) on a
                  bounded sample of the same workload, rank 0 only.
+  torch_eager_baseline : the same chain restated with stock eager PyTorch ops on the same GPU
+                 (oracle/torch_eager.py), bounded sample, rank 0 only -- the "torch-CUDA path" comparator.
 
 Multi-GPU (torchrun, one rank per GPU): pairs are independent, so each rank processes its own
 shard of pairs (weak scaling); torch.distributed is used for the barrier and the max-over-ranks
@@ -366,6 +368,26 @@ def run_ours(args):
     cores = os.cpu_count() or 1
     n_cpu = args.cpu_pairs
     cpu_rate, cpu_dt = cpu_oracle_rate(n_cpu, warmup=1)
+    # ---- stock eager PyTorch on the same GPU (restatement of the reference's op chain, bounded sample) ----
+    torch_eager = None
+    if args.torch_pairs > 0:
+        from oracle import torch_eager as E
+        second = E.IterCWS(SHAPE, WIND // 2, OVERLAP // 2, dev)
+        E.two_pass_cws(fa[0], fb[0], WIND, OVERLAP, second)              # warm-up (cuFFT plans, allocator)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for i in range(args.torch_pairs):
+            E.two_pass_cws(fa[i % B], fb[i % B], WIND, OVERLAP, second)
+        torch.cuda.synchronize(dev)
+        te = time.perf_counter() - t0
+        torch_eager = {"value": args.torch_pairs / te, "unit": "pairs/s", "kind": "port",
+                       "what": "oracle/torch_eager.py: the reference's op chain restated with stock eager PyTorch "
+                               "(aten + cuFFT kernels, 3 D2H syncs and host SciPy splines per pass) on this GPU, "
+                               "frames resident; the reference's own sources cannot travel to the GPU box",
+                       "sample": f"{args.torch_pairs} 4MP pairs, 2-pass CWS, {te:.2f} s"}
+        del second
+        torch.cuda.empty_cache()
+
     line = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -384,6 +406,7 @@ def run_ours(args):
         "clocks": clocks, "roofline": roofline,
         "cpu_baseline": {"value": cpu_rate, "unit": "pairs/s", "cores": cores, "kind": "port",
                          "sample": f"{n_cpu} 4MP pairs, 2-pass CWS pass functions (CPU oracle, scipy.fft workers=-1), {cpu_dt:.1f} s"},
+        "torch_eager_baseline": torch_eager,
         "check": {"median_u_px": med_u, "median_v_px": med_v, "imposed": [3.3, -2.2]},
     }
     print(json.dumps(line))
@@ -399,6 +422,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs-per-step", type=int, default=PAIRS_PER_STEP)
     ap.add_argument("--cpu-pairs", type=int, default=4, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--torch-pairs", type=int, default=24,
+                    help="size of the bounded eager-PyTorch-on-GPU sample (0 = skip)")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: re-launch under torchrun, one rank per GPU

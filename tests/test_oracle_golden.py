@@ -183,3 +183,41 @@ def test_multipass_scale_1p5_function_boundary(golden, mode):
             err = np.abs(got - g[f"{mode}_p{it}_{key}"])
             assert np.quantile(err, 0.98) < TOL32 and np.quantile(err, 0.995) < 1e-3
         x, y = x1, y1
+
+
+# ------------------------------------------------------------------------------------------
+# oracle/torch_eager.py: the eager-PyTorch restatement that bench.py times on the GPU as the
+# "stock torch-CUDA path" comparator.  Pinned here with device="cpu".
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,zero", [("uniform", False), ("vortex", True)])
+def test_torch_eager_pass1(golden, kind, zero):
+    import torch
+    from oracle import torch_eager as E
+    g = golden("pass1.npz")
+    a, b = cases.small_pair(seed=1, kind=kind, zero_patch=zero)
+    for w, o in ((64, 32), (32, 16)):
+        u, v, x, y, m = E.pass_first(torch.from_numpy(a), torch.from_numpy(b), w, o)
+        assert np.array_equal(m, g[f"{kind}_{w}_{o}_mask"])
+        assert np.array_equal(x, g[f"{kind}_{w}_{o}_x"]) and np.array_equal(y, g[f"{kind}_{w}_{o}_y"])
+        assert np.abs(u - g[f"{kind}_{w}_{o}_u"]).max() < TOL64 and np.abs(v - g[f"{kind}_{w}_{o}_v"]).max() < TOL64
+
+
+@pytest.mark.parametrize("kind", ["uniform", "vortex"])
+def test_torch_eager_cws_pass(golden, kind):
+    import torch
+    from oracle import torch_eager as E
+    g = golden("multipass_CWS.npz")
+    a, b = cases.small_pair(seed=2, kind=kind)
+    ta, tb = torch.from_numpy(a), torch.from_numpy(b)
+    x, y = O.get_coordinates(a.shape, 64, 32)
+    u0, v0, m0 = (g[f"{kind}_p0_{k}"].copy() for k in ("u", "v", "mask"))
+    fn = E.IterCWS(a.shape, 32, 16, torch.device("cpu"))
+    u, v, x1, y1, m = fn(ta, tb, x, y, u0, v0, m0)
+    assert np.array_equal(m, g[f"{kind}_p1_mask"])
+    assert np.array_equal(x1, g[f"{kind}_p1_x"]) and np.array_equal(y1, g[f"{kind}_p1_y"])
+    for got, key in ((u, "u"), (v, "v")):
+        err = np.abs(got - g[f"{kind}_p1_{key}"])
+        assert np.quantile(err, 0.99) < TOL32 and err.max() < 1e-3
+    # and the chained driver reproduces pass 1 -> pass 2
+    u2, v2, _, _, m2 = E.two_pass_cws(ta, tb)
+    assert u2.shape == u.shape and (m2 != m).mean() < 0.02
