@@ -16,7 +16,7 @@
  *   - window index n = row * n_cols + col (row-major), pair index outermost: g = pair * n + n;
  *   - interrogation windows of 16, 32 or 64 px run the fused in-register FFT kernels; any other
  *     EVEN size from 4 to 128 px runs a general kernel (direct DFT in shared memory, same
- *     semantics, ~30x slower per window; scratch memory comes from cudaMallocAsync on `stream`);
+ *     semantics, ~15-30x slower per window; scratch memory comes from cudaMallocAsync on `stream`);
  *     odd sizes and sizes above 128 px return PIVB200_E_WINDOW.  There is no CPU fallback
  *     anywhere in this library.
  */

@@ -4,11 +4,11 @@
 // The fused in-register FFT kernels (piv_fused.cuh) exist for 16 / 32 / 64 px only.  Everything else
 // takes this path: one CTA per window reads the (shifted) window straight from the frames with the
 // reference's flat-index addressing (PB:147-216), evaluates the circular cross-correlation with a
-// direct O(w^3) DFT in shared memory (both frames packed into one complex transform, FP32, twiddles
+// direct DFT in shared memory (one radix-2/4 split, O(w^3 / r)) (both frames packed into one complex transform, FP32, twiddles
 // from a table computed in FP64), subtracts the minimum (PB:518/724/796) and writes the fft-shifted
 // map to a scratch buffer; correlation_to_displacement (corr_to_disp_kernel, PB:346-422) and the
 // predictor glue (PB:728-738 / 800-810) follow as two small kernels.  Correct for every geometry,
-// roughly 30x slower per window than the fused kernels -- a completeness path, not the headline one.
+// roughly 15-30x slower per window than the fused kernels -- a completeness path, not the headline one.
 //
 // Included by pivb200.cu (needs corr_to_disp_kernel and grid_for).
 #pragma once
@@ -81,40 +81,89 @@ __device__ __forceinline__ float block_reduce(float v, float* red, int op) {   /
     return r;
 }
 
-// In-place DFT of every line of Z (rows: elements Z[L][x]; columns: Z[x][L]); a warp owns a line, lane l
-// produces the outputs k = l, l + 32, ... .  conj = inverse transform (unnormalised).
-__device__ __forceinline__ void generic_lines(float2* Z, const float2* tw, int w, int pitch, bool columns, bool conj) {
+// In-place DFT of every line of Z (rows: elements Z[L][x]; columns: Z[x][L]); a warp owns a line.
+// One decimation-in-time split by r = 4 (w >= 96, 4 | w), 2, or 1 keeps the lanes busy and divides the
+// O(w^2) work per line by r:  S_q[k'] = sum_x' z[r x' + q] W_m^{x' k'}  (m = w / r, direct sums, lane l owns
+// k' = l, l + 32, ...), then X[k' + m t] = sum_q W_r^{q t} (W_w^{q k'} S_q[k']).  conj = inverse transform
+// (unnormalised).  Four accumulators per lane in every case: (r, outputs per lane) = (1, 4), (2, 2), (4, 1).
+__device__ __forceinline__ float2 gmul(float2 a, float2 t) {
+    return make_float2(fmaf(a.x, t.x, -a.y * t.y), fmaf(a.x, t.y, a.y * t.x));
+}
+template <int R>
+__device__ __forceinline__ void generic_lines_r(float2* Z, const float2* tw, int w, int pitch, bool columns, bool conj) {
+    constexpr int J = 4 / R;                     // outputs k' per lane
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int es = columns ? pitch : 1, ls = columns ? 1 : pitch;
+    const int m = w / R;
+    const float sgn = conj ? -1.f : 1.f;
     for (int L = warp; L < w; L += kGenericThreads / 32) {
         float2* line = Z + L * ls;
-        float2 acc[4];
-        int idx[4];
+        float2 acc[R][J];
+        int idx[J], stepk[J];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { acc[j] = make_float2(0.f, 0.f); idx[j] = 0; }
-        for (int x = 0; x < w; ++x) {
-            const float2 v = line[x * es];                              // broadcast read
+        for (int j = 0; j < J; ++j) {
+            idx[j] = 0;
+            stepk[j] = (R * (lane + 32 * j)) % w;                          // W_m^{k'} = W_w^{R k'}
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = lane + 32 * j;
-                if (k < w) {
+            for (int q = 0; q < R; ++q) acc[q][j] = make_float2(0.f, 0.f);
+        }
+        for (int x = 0; x < m; ++x) {
+            float2 v[R];
+#pragma unroll
+            for (int q = 0; q < R; ++q) v[q] = line[(R * x + q) * es];       // broadcast reads
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                if (lane + 32 * j < m) {
                     float2 t = tw[idx[j]];
-                    if (conj) t.y = -t.y;
-                    acc[j].x = fmaf(v.x, t.x, fmaf(-v.y, t.y, acc[j].x));
-                    acc[j].y = fmaf(v.x, t.y, fmaf(v.y, t.x, acc[j].y));
-                    idx[j] += k;
+                    t.y *= sgn;
+#pragma unroll
+                    for (int q = 0; q < R; ++q) {
+                        acc[q][j].x = fmaf(v[q].x, t.x, fmaf(-v[q].y, t.y, acc[q][j].x));
+                        acc[q][j].y = fmaf(v[q].x, t.y, fmaf(v[q].y, t.x, acc[q][j].y));
+                    }
+                    idx[j] += stepk[j];
                     if (idx[j] >= w) idx[j] -= w;
                 }
             }
         }
-        __syncwarp();                                                    // the whole line was read
+        __syncwarp();                                                        // the whole line was read
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < J; ++j) {
             const int k = lane + 32 * j;
-            if (k < w) line[k * es] = acc[j];
+            if (k >= m) continue;
+            float2 T[R];
+            T[0] = acc[0][j];
+#pragma unroll
+            for (int q = 1; q < R; ++q) {
+                float2 t = tw[(q * k) % w];
+                t.y *= sgn;
+                T[q] = gmul(acc[q][j], t);
+            }
+            if constexpr (R == 1) {
+                line[k * es] = T[0];
+            } else if constexpr (R == 2) {
+                line[k * es] = make_float2(T[0].x + T[1].x, T[0].y + T[1].y);
+                line[(k + m) * es] = make_float2(T[0].x - T[1].x, T[0].y - T[1].y);
+            } else {
+                // radix-4 butterfly with W_4 = -i (forward) or +i (inverse)
+                const float2 s02 = make_float2(T[0].x + T[2].x, T[0].y + T[2].y);
+                const float2 d02 = make_float2(T[0].x - T[2].x, T[0].y - T[2].y);
+                const float2 s13 = make_float2(T[1].x + T[3].x, T[1].y + T[3].y);
+                const float2 d13 = make_float2(T[1].x - T[3].x, T[1].y - T[3].y);
+                const float2 rot = make_float2(sgn * d13.y, -sgn * d13.x);     // -i d13 (forward), +i d13 (inverse)
+                line[k * es] = make_float2(s02.x + s13.x, s02.y + s13.y);
+                line[(k + m) * es] = make_float2(d02.x + rot.x, d02.y + rot.y);
+                line[(k + 2 * m) * es] = make_float2(s02.x - s13.x, s02.y - s13.y);
+                line[(k + 3 * m) * es] = make_float2(d02.x - rot.x, d02.y - rot.y);
+            }
         }
     }
     __syncthreads();
+}
+__device__ __forceinline__ void generic_lines(float2* Z, const float2* tw, int w, int pitch, bool columns, bool conj) {
+    if (w % 4 == 0 && w >= 96) generic_lines_r<4>(Z, tw, w, pitch, columns, conj);
+    else if (w >= 16) generic_lines_r<2>(Z, tw, w, pitch, columns, conj);
+    else generic_lines_r<1>(Z, tw, w, pitch, columns, conj);
 }
 
 __global__ void __launch_bounds__(kGenericThreads) generic_corr_kernel(const GenericParams p) {
