@@ -125,3 +125,26 @@ def test_mixed_plan_full_size(T):
     ok = ~m[0].bool()
     assert ok.float().mean() > 0.95
     assert abs(float(u[0][ok].median()) - 3.3) < 0.1 and abs(float(v[0][ok].median()) + 2.2) < 0.1
+
+
+def test_general_path_batches_pitch_and_no_validation(T):
+    """Batch of pairs, frames that are strided views (pitch > width), and validate=False all give what a
+    single contiguous pair gives."""
+    a, b = cases.small_pair(seed=3, kind="vortex", zero_patch=True)
+    fa, fb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    plan = T.PIVPlan(a.shape, 48, 24, 2, "CWS", 2.0, device="cuda:0")          # 48 -> 24 px
+    u1, v1, m1 = (t.clone() for t in plan.run(fa, fb))
+    wide_a = torch.zeros((3, a.shape[0], a.shape[1] + 16), dtype=torch.uint8, device="cuda")
+    wide_b = torch.zeros_like(wide_a)
+    wide_a[:, :, :a.shape[1]] = torch.stack([fa, fb, fa])
+    wide_b[:, :, :a.shape[1]] = torch.stack([fb, fa, fb])
+    u3, v3, m3 = plan.run(wide_a[:, :, :a.shape[1]], wide_b[:, :, :a.shape[1]])
+    for i in (0, 2):
+        assert torch.equal(u3[i], u1[0]) and torch.equal(v3[i], v1[0]) and torch.equal(m3[i], m1[0])
+    un, vn, mn = plan.run(fa, fb, validate=False)
+    # without validation there is no mask-driven replacement, but vectors the first pass keeps are the same
+    assert torch.isfinite(un).all() and torch.isfinite(vn).all()
+    u, v, x, y, m = T.extended_search_area_piv(fa, fb, window_size=48, overlap=24, validate=False)
+    assert m is None
+    ou, ov, _, _, _ = O.extended_search_area_piv(a, b, 48, 24, validate=False)
+    assert np.quantile(np.abs(u - ou), 0.9) < 2e-5 and np.quantile(np.abs(v - ov), 0.9) < 2e-5
