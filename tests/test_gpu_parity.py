@@ -491,3 +491,48 @@ def test_native_library_is_what_ran():
     with open("/proc/self/maps") as fh:
         assert any("libpivb200.so" in line for line in fh)
     assert os.path.isfile(_lib.LIB_PATH)
+
+
+def test_tensor_core_row_transform_variant():
+    """PIVB200_TC=1 routes the 64 px first pass through the experimental kernel variant whose row transform
+    runs on the tensor cores (tcgen05.mma, fp16 operands, hi + lo split DFT matrix).
+    The switch is read once per process, hence the subprocess.  Same bars as the FP32 variant."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, "tests"); sys.path.insert(0, "tests/golden"); sys.path.insert(0, ".")
+import cases, gpu_util as G
+from oracle import piv_oracle as O
+from test_gpu_parity import check_field
+from torchpiv_b200 import _lib
+g = np.load("tests/golden/pass1.npz")
+for kind, zero in (("uniform", False), ("vortex", True)):
+    a, b = cases.small_pair(seed=1, kind=kind, zero_patch=zero)
+    for w, o in ((64, 32), (64, 48)):
+        u, v, m = G.pass_first(a, b, w, o)
+        stash = {}
+        O.extended_search_area_piv(a, b, w, o, validate=True, stash=stash)
+        ref = [g[f"{kind}_{w}_{o}_{k}"] for k in ("u", "v", "mask")]
+        check_field(u[0], v[0], m[0], *ref, stash["corr"])
+        assert np.array_equal(m[0], ref[2])
+        assert max(np.abs(u[0] - ref[0]).max(), np.abs(v[0] - ref[1]).max()) < 1e-4
+# batch of pairs: every group of four warps and both accumulator tiles are exercised
+import torch, torchpiv_b200 as T
+from torchpiv_b200 import synth
+a, b = synth.particle_pair((512, 512), synth.uniform_shift(3.3, -2.2), seed=3)
+fa = torch.from_numpy(a).cuda()[None].expand(5, -1, -1).contiguous()
+fb = torch.from_numpy(b).cuda()[None].expand(5, -1, -1).contiguous()
+plan = T.PIVPlan(a.shape, 64, 32, 2, "CWS", 2.0, device="cuda:0")
+u, v, m = plan.run(fa, fb)
+ou, ov, _, _, om, _ = O.piv_passes(a, b, 64, 32, 2, "CWS")
+for i in range(5):
+    assert torch.equal(u[i], u[0]) and torch.equal(m[i], m[0])
+ok = ~om & ~m[0].cpu().numpy().astype(bool)
+assert np.quantile(np.abs(u[0].cpu().numpy() - ou)[ok], 0.99) < 1e-4
+print("TC-OK")
+'''
+    env = dict(os.environ, PIVB200_TC="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "TC-OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

@@ -67,6 +67,9 @@ template <int W>
 static int launch_w(int loader, int sink, const CUtensorMap& ta, const CUtensorMap& tb,
                     const PassParams& p, cudaStream_t stream) {
     if (sink == SK_DISP && loader == LD_FRAME_INT) return launch_one<W, LD_FRAME_INT, SK_DISP>(ta, tb, p, stream);
+    if constexpr (W == 64) {
+        if (sink == SK_DISP && loader == LD_FRAME_TC) return launch_one<W, LD_FRAME_TC, SK_DISP>(ta, tb, p, stream);
+    }
     if (sink == SK_DISP && loader == LD_FRAME_ALN) return launch_one<W, LD_FRAME_ALN, SK_DISP>(ta, tb, p, stream);
     if (sink == SK_WIN && loader == LD_FRAME_ALN) return launch_one<W, LD_FRAME_ALN, SK_WIN>(ta, tb, p, stream);
     if (sink == SK_DISP && loader == LD_FRAME_CWS) return launch_one<W, LD_FRAME_CWS, SK_DISP>(ta, tb, p, stream);

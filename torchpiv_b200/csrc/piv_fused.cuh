@@ -28,6 +28,7 @@
 // buffer -- and it also receives the TMA tiles, so 12 (W=64) to 24 (W=16) warps are resident per SM.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cfloat>
 #include <cstdint>
@@ -61,8 +62,9 @@ struct Geo {
 
 template <int W, int LOADER>
 struct Tile {
-    static constexpr bool kFrame = (LOADER == LD_FRAME_INT || LOADER == LD_FRAME_CWS || LOADER == LD_FRAME_ALN);
-    static constexpr bool kAligned = (LOADER == LD_FRAME_ALN);
+    static constexpr bool kFrame = (LOADER == LD_FRAME_INT || LOADER == LD_FRAME_CWS || LOADER == LD_FRAME_ALN ||
+                                    LOADER == LD_FRAME_TC);
+    static constexpr bool kAligned = (LOADER == LD_FRAME_ALN || LOADER == LD_FRAME_TC);
     // TMA box.  The global start address of a box row must be 16-byte aligned (an unaligned x
     // coordinate faults as "illegal instruction" on sm_100a), so the box starts at the window's
     // x origin rounded DOWN to 16 and is 16 bytes wider than the bytes that are used; the row
@@ -134,6 +136,13 @@ struct Smem {
     static constexpr int STRIDE = ((TOTAL + T::BASE_ALIGN - 1) / T::BASE_ALIGN) * T::BASE_ALIGN;
     static_assert(G::NW == 1 || T::BASE_ALIGN <= 256, "window buffers are 256-byte aligned inside a warp's slot");
     static constexpr int SMEM_MAX = 232448 - 1024;    // 227 KB opt-in limit per CTA minus the static allocation
+    // tensor-core row transform (LD_FRAME_TC): CTA-wide area in front of the warp slots -- the DFT matrix
+    // (hi and lo halves, 64 x 64 fp16 each) and, per group of four warps, two 128 x 64 fp16 operand tiles
+    static constexpr bool kTC = (LOADER == LD_FRAME_TC);
+    static constexpr int TC_GROUPS = 2;               // 2 x (128 accumulator + 128 parking) TMEM columns = 512
+    static constexpr int TC_TW_OFF = 0;               // [2][8 KB]
+    static constexpr int TC_A_OFF = 16384;            // [TC_GROUPS][2][16 KB]
+    static constexpr int SHARED = kTC ? TC_A_OFF + TC_GROUPS * 2 * 16384 : 0;
     // warps per CTA: bounded by shared memory, by the register file (launch bounds) and by the 512
     // TMEM columns (4 lane quarters x 512 / TCOLS warps)
 #ifndef PIVB200_W64_WARPS
@@ -145,12 +154,14 @@ struct Smem {
 #ifndef PIVB200_W16_WARPS
 #define PIVB200_W16_WARPS 24
 #endif
-    static constexpr int WARP_CAP = (W == 64) ? PIVB200_W64_WARPS : (W == 32 ? PIVB200_W32_WARPS : PIVB200_W16_WARPS);
+    static constexpr int WARP_CAP = kTC ? 4 * TC_GROUPS
+                                        : ((W == 64) ? PIVB200_W64_WARPS : (W == 32 ? PIVB200_W32_WARPS : PIVB200_W16_WARPS));
     static constexpr int TMEM_CAP = 4 * (512 / G::TCOLS);
-    static constexpr int BY_SMEM = SMEM_MAX / STRIDE;
+    static constexpr int BY_SMEM = (SMEM_MAX - SHARED) / STRIDE;
     static constexpr int NWARPS0 = BY_SMEM < WARP_CAP ? BY_SMEM : WARP_CAP;
     static constexpr int NWARPS = NWARPS0 < TMEM_CAP ? NWARPS0 : TMEM_CAP;
-    static constexpr int CTA_BYTES = NWARPS * STRIDE;
+    static constexpr int CTA_BYTES = SHARED + NWARPS * STRIDE;
+    static_assert(!kTC || (W == 64 && NWARPS == 4 * TC_GROUPS), "the tensor-core row transform is built for 64 px windows");
 };
 
 // ----------------------------------------------------------------------------------------
@@ -361,6 +372,42 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float2 (&v)[16]) {
         : "memory");
 }
 
+// ----------------------------------------------------------------------------------------
+// tcgen05.mma (kind::f16, single CTA): D[128 x 64, FP32, TMEM] (+)= A[128 x 64 fp16] * B[64 x 64 fp16]^T, both
+// operands K-major in the canonical SWIZZLE_128B shared-memory layout (rows of 128 bytes, atoms of 8 rows,
+// 16-byte chunk c of row r stored at chunk c ^ (r & 7)).  Bit layouts: cute/arch/mma_sm100_desc.hpp.
+// ----------------------------------------------------------------------------------------
+__host__ __device__ constexpr int sw128_offset(int row, int chunk) {
+    return (row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return static_cast<uint64_t>((saddr >> 4) & 0x3fff)        // start address >> 4
+           | (static_cast<uint64_t>(1) << 16)                  // leading byte offset: unused for swizzled K-major
+           | (static_cast<uint64_t>(1024 >> 4) << 32)          // stride byte offset: 8 rows x 128 B
+           | (static_cast<uint64_t>(1) << 46)                  // descriptor version (sm_100)
+           | (static_cast<uint64_t>(2) << 61);                 // SWIZZLE_128B
+}
+// instruction descriptor: C = F32, A = B = F16, K-major, N = 64 (>> 3 at bit 17), M = 128 (>> 4 at bit 24)
+constexpr uint32_t kUmmaIdesc = (1u << 4) | (static_cast<uint32_t>(64 >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(kUmmaIdesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// four uint8 of `w` -> two half2 (exact): byte b becomes the fp16 bit pattern 0x64bb = 1024 + b, minus 1024
+__device__ __forceinline__ void u8x4_to_h2x2(uint32_t w, uint32_t& lo, uint32_t& hi) {
+    const uint32_t a = __byte_perm(w, 0x64646464u, 0x4140), b = __byte_perm(w, 0x64646464u, 0x4342);
+    const __half2 k = __floats2half2_rn(1024.f, 1024.f);
+    const __half2 ha = __hsub2(*reinterpret_cast<const __half2*>(&a), k), hb = __hsub2(*reinterpret_cast<const __half2*>(&b), k);
+    lo = *reinterpret_cast<const uint32_t*>(&ha);
+    hi = *reinterpret_cast<const uint32_t*>(&hb);
+}
+
 // Parking order of a column spectrum.  After the forward column FFT bin q sits in register slot
 // pos(q) (digit reversed); the inverse transform (same code, same register view) wants element q in
 // slot q.  The product conj(A^) B^ therefore moves its result from slot pos(q) to slot q, which can be
@@ -448,7 +495,9 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;                      // <= S::NWARPS (launcher)
-    unsigned char* smem = smem_cta + warp * S::STRIDE;       // this warp's private slot
+    unsigned char* smem = smem_cta + S::SHARED + warp * S::STRIDE;       // this warp's private slot
+    constexpr bool kTC = S::kTC;
+    __shared__ __align__(8) uint64_t tc_bar_sh[S::TC_GROUPS];                // MMA completion, one per group of four warps
     const int n_total = static_cast<int>(p.n_total);
     const int njobs = (n_total + NW - 1) / NW;
     const int job_stride = gridDim.x * nwarps;
@@ -460,7 +509,31 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
         tmem_fence_before();
         __syncthreads();
         tmem_fence_after();
-        tpark = tmem_base_sh + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>((warp >> 2) * G::TCOLS);
+        // parking area of this warp: its 32 lanes, TCOLS columns per group of four warps (with the tensor-core
+        // row transform a group owns 2 TCOLS columns: accumulators first, parking after them)
+        tpark = tmem_base_sh + (static_cast<uint32_t>((warp & 3) * 32) << 16) +
+                static_cast<uint32_t>(kTC ? (warp >> 2) * 2 * G::TCOLS + G::TCOLS : (warp >> 2) * G::TCOLS);
+    }
+    if constexpr (kTC) {
+        // DFT matrix B[n][x], n = output column: n = 2k -> 2 cos(2 pi k x / W) (k = 0..W/2-1), n = 2k + 1 ->
+        // -2 sin(2 pi k x / W) (k >= 1), n = 1 -> 2 cos(pi x) (bin W/2): column pairs (2k, 2k+1) are the X entries
+        // (2 Re R[k], 2 Im R[k]) with bins 0 and W/2 sharing slot 0, exactly what the FP32 row step stores.
+        // fp16 hi + lo split (two MMAs into one accumulator) gives FP32-level accuracy.
+        for (int e = threadIdx.x; e < W * W; e += blockDim.x) {
+            const int n = e / W, xx = e - n * W, k = n >> 1;
+            double sn, cs;
+            sincospi(2.0 * ((k * xx) % W) / W, &sn, &cs);
+            double v = (n & 1) ? -2.0 * sn : 2.0 * cs;
+            if (n == 1) v = (xx & 1) ? -2.0 : 2.0;
+            const __half hi = __double2half(v);
+            const __half lo = __double2half(v - static_cast<double>(__half2float(hi)));
+            const int off = sw128_offset(n, xx >> 3) + (xx & 7) * 2;
+            *reinterpret_cast<__half*>(smem_cta + S::TC_TW_OFF + off) = hi;
+            *reinterpret_cast<__half*>(smem_cta + S::TC_TW_OFF + 8192 + off) = lo;
+        }
+        if (threadIdx.x < S::TC_GROUPS) mbar_init(smem_u32(&tc_bar_sh[threadIdx.x]), 1);
+        fence_proxy_async();
+        __syncthreads();
     }
     if constexpr (T::kFrame) {
         if (lane == 0) mbar_init(bar, 1);
@@ -570,7 +643,61 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
             if (s == 0 || s == 2) {
                 const int frame = s >> 1;
                 stage_wait(frame);
-                if constexpr (LOADER == LD_FRAME_INT || LOADER == LD_FRAME_ALN) {
+                if constexpr (kTC) {
+                    // rows l and l + W/2 of this warp's window -> fp16 rows 32 q + l of the group's two operand
+                    // tiles (q = this warp's TMEM lane quarter), so that after the MMAs lane l of THIS warp finds
+                    // the spectrum of row l in accumulator columns [0, W) and of row l + W/2 in [W, 2 W)
+                    const int grp = warp >> 2, q = warp & 3;
+                    unsigned char* const tA = smem_cta + S::TC_A_OFF + grp * 32768;
+                    uint32_t w0[W / 4], w1[W / 4];
+                    load_row_words<W, LOADER, W / 4>(region, l, 0, w0);
+                    load_row_words<W, LOADER, W / 4>(region, l + HALF, 0, w1);
+                    const int arow = 32 * q + l;
+                    static_for<0, W / 8>([&](auto cc) {
+                        constexpr int c = decltype(cc)::value;          // 8 pixels = 2 words -> one 16-byte chunk of fp16
+                        uint4 h0, h1;
+                        u8x4_to_h2x2(w0[2 * c], h0.x, h0.y);
+                        u8x4_to_h2x2(w0[2 * c + 1], h0.z, h0.w);
+                        u8x4_to_h2x2(w1[2 * c], h1.x, h1.y);
+                        u8x4_to_h2x2(w1[2 * c + 1], h1.z, h1.w);
+                        *reinterpret_cast<uint4*>(tA + sw128_offset(arow, c)) = h0;
+                        *reinterpret_cast<uint4*>(tA + 16384 + sw128_offset(arow, c)) = h1;
+                    });
+                    fence_proxy_async();                    // generic-proxy stores -> visible to the tensor core
+                    tmem_fence_before();
+                    asm volatile("bar.sync %0, 128;" ::"r"(8 + grp) : "memory");
+                    const uint32_t gbar = smem_u32(&tc_bar_sh[grp]);
+                    const uint32_t tacc = tmem_base_sh + static_cast<uint32_t>(grp * 2 * G::TCOLS);
+                    if (q == 0 && lane == 0) {
+                        tmem_fence_after();
+                        const uint64_t dA1 = umma_desc_sw128(smem_u32(tA)), dA2 = umma_desc_sw128(smem_u32(tA + 16384));
+                        const uint64_t dBh = umma_desc_sw128(smem_u32(smem_cta + S::TC_TW_OFF));
+                        const uint64_t dBl = umma_desc_sw128(smem_u32(smem_cta + S::TC_TW_OFF + 8192));
+                        static_for<0, 2>([&](auto hc) {
+                            constexpr int half_id = decltype(hc)::value;     // rows l (tile 1) / rows l + W/2 (tile 2)
+                            const uint64_t dA = half_id ? dA2 : dA1;
+                            static_for<0, W / 16>([&](auto kc) {             // UMMA K = 16 fp16 = 32 bytes = +2 in the address field
+                                constexpr int k = decltype(kc)::value;
+                                umma_f16(tacc + half_id * W, dA + 2 * k, dBh + 2 * k, k > 0);
+                            });
+                            static_for<0, W / 16>([&](auto kc) {
+                                constexpr int k = decltype(kc)::value;
+                                umma_f16(tacc + half_id * W, dA + 2 * k, dBl + 2 * k, 1);
+                            });
+                        });
+                        umma_commit(gbar);
+                    }
+                    mbar_wait(gbar, static_cast<uint32_t>(frame));       // two commits per job: parity = frame
+                    tmem_fence_after();
+                    const uint32_t tsrc = tacc + (static_cast<uint32_t>(q * 32) << 16);
+                    static_for<0, W / 16>([&](auto cc) {
+                        constexpr int c = decltype(cc)::value;           // 32 columns = 16 (re, im) pairs
+                        float2 v[16];
+                        tmem_ld16(tsrc + 32 * c, v);
+                        static_for<0, 16>([&](auto ic) { constexpr int i = decltype(ic)::value; x[16 * c + i] = v[i]; });
+                    });
+                    tmem_wait_ld();
+                } else if constexpr (LOADER == LD_FRAME_INT || LOADER == LD_FRAME_ALN) {
                     const TileDesc* desc = reinterpret_cast<const TileDesc*>(smem + S::TD_OFF);
                     const int d = desc[wi * 2 + frame].d;
                     uint32_t w0[W / 4], w1[W / 4];
@@ -721,10 +848,24 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                 __syncwarp();                   // Q fully read before the map overwrites it
             }
 
-            if constexpr (SINK != SK_WIN) F::run(x);
+            if constexpr (kTC) {
+                if (s != 0 && s != 2) F::run(x);            // the row transforms came from the tensor cores
+            } else if constexpr (SINK != SK_WIN) {
+                F::run(x);
+            }
 
             // ---------------------------------------------------------------- store
-            if (s == 0 || s == 2) {
+            if (kTC && (s == 0 || s == 2)) {
+                // x[0 .. W/2) = spectrum of row l, x[W/2 .. W) = of row l + W/2, already in the X layout
+                float2* X1 = Xw + l * PX;
+                float2* X2 = Xw + (l + HALF) * PX;
+                static_for<0, HALF>([&](auto kc_) {
+                    constexpr int k = decltype(kc_)::value;
+                    X1[k] = x[k];
+                    X2[k] = x[HALF + k];
+                });
+                __syncwarp();
+            } else if (s == 0 || s == 2) {
                 // z = r1 + i r2: R1[k] = Z[k] + conj Z[W-k], R2[k] = -i (Z[k] - conj Z[W-k])  (x2, folded into K);
                 // bins 0 and W/2 are real and share one complex slot
                 float2* X1 = Xw + l * PX;

@@ -12,6 +12,11 @@ enum Loader : int {
     LD_FRAME_ALN = 4    // LD_FRAME_INT without shifts on a grid whose step is a multiple of 16 px (the usual
                         // first pass): every tile row starts 16-byte aligned, so the TMA box is exactly the
                         // window and the loader needs no realignment network
+    ,
+    LD_FRAME_TC = 5     // LD_FRAME_ALN for 64 px windows with the ROW transform on the tensor cores: the uint8 rows
+                        // become fp16 operands (exact) of tcgen05.mma against a hi + lo split DFT matrix, the
+                        // spectra come back from tensor memory -- no row FFT and no u8 -> f32 conversion on the
+                        // FP32 pipe
 };
 
 enum Sink : int {

@@ -124,12 +124,15 @@ static int run_frame_pass(const uint8_t* fa, const uint8_t* fb, int n_pairs, lon
     // aligned in every row: the aligned loader skips the realignment network (PIVB200_NO_ALIGNED=1: A/B knob)
     static const bool no_aligned = [] { const char* e = getenv("PIVB200_NO_ALIGNED"); return e && e[0] == '1'; }();
     if (loader == LD_FRAME_INT && p.sxi == nullptr && p.step % 16 == 0 && !no_aligned) loader = LD_FRAME_ALN;
+    // 64 px first pass: the row transform runs on the tensor cores (PIVB200_TC=0: keep it on the FP32 pipe)
+    static const bool use_tc = [] { const char* e = getenv("PIVB200_TC"); return e != nullptr && e[0] == '1'; }();
+    if (loader == LD_FRAME_ALN && wind == 64 && sink == SK_DISP && use_tc) loader = LD_FRAME_TC;
     CUtensorMap ta, tb;
     memset(&ta, 0, sizeof(ta));
     memset(&tb, 0, sizeof(tb));
     p.use_tma = tma_ok(fa, fb, n_pairs, pair_stride, pitch) ? 1 : 0;
     if (p.use_tma) {
-        const int bx = (loader == LD_FRAME_ALN) ? wind : wind + 16;   // = Tile<W, LOADER>::BX
+        const int bx = (loader == LD_FRAME_ALN || loader == LD_FRAME_TC) ? wind : wind + 16;   // = Tile<W, LOADER>::BX
         const int by = (loader == LD_FRAME_CWS) ? wind + 1 : wind;
         if (make_frame_map(&ta, fa, n_pairs, pair_stride, H, W, pitch, bx, by) ||
             make_frame_map(&tb, fb, n_pairs, pair_stride, H, W, pitch, bx, by))
