@@ -26,6 +26,13 @@
 //   E   min / argmax / neighbours / second peak on the fft-shifted map -> u, v, mask
 // Shared memory per window is W*(H+1)*8 bytes (16.5 KB for W = 64) -- half of a complex W x W
 // buffer -- and it also receives the TMA tiles, so 12 (W=64) to 24 (W=16) warps are resident per SM.
+//
+// Loaders (template parameter LOADER, piv_params.h): LD_FRAME_ALN (unshifted windows on a 16-px aligned
+// grid: TMA box = window), LD_FRAME_INT (integer shifts: box 16 B wider, rows re-aligned in registers),
+// LD_FRAME_CWS (float shifts: separable bilinear taps, packed FP32), LD_EXPL_* (materialised windows, function-
+// level API) and the experimental LD_FRAME_TC (64 px first pass whose row transform Ra / Rb runs on the
+// tensor cores: groups of four warps stage fp16 operand tiles, one thread issues tcgen05.mma, the spectra
+// come back from TMEM already in the X layout).
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
