@@ -478,6 +478,50 @@ __device__ __noinline__ void gather_border_tile(const PassParams& p, const TileD
     }
 }
 
+// Window that only PARTLY leaves the frame (the common border case: one or two columns / rows): the tile is
+// fetched by TMA like an interior one -- out-of-frame elements arrive as zeros -- and only those elements are
+// then patched with the reference's flat-index values.  Same element rule as gather_border_tile; the tile
+// layout is the TMA one (row data starts at byte d = ox & 15).
+constexpr int kPatchFlag = 256;
+template <int W, int LOADER>
+__device__ __noinline__ void patch_border_tile(const PassParams& p, const TileDesc dsc, unsigned char* tile,
+                                               int frame, int lane) {
+    using T = Tile<W, LOADER>;
+    const unsigned char* f = (frame ? p.fb : p.fa) + dsc.pair * p.pair_stride;
+    const int last_y = p.H - 1, last_x = p.Wf - 1, d = dsc.d & 15;
+    const int ntop = clampi(-dsc.oy, 0, T::BY), nbot = clampi(dsc.oy + T::BY - p.H, 0, T::BY - ntop);
+    const int nleft = clampi(-dsc.ox, 0, T::USED), nright = clampi(dsc.ox + T::USED - p.Wf, 0, T::USED - nleft);
+    const int rows_oob = ntop + nbot, cols_oob = nleft + nright;
+    const int n_rowpart = rows_oob * T::USED, n_all = n_rowpart + (T::BY - rows_oob) * cols_oob;
+#pragma unroll 1
+    for (int e = lane; e < n_all; e += 32) {
+        int i, jj;
+        if (e < n_rowpart) {
+            const int ri = e / T::USED;
+            jj = e - ri * T::USED;
+            i = ri < ntop ? ri : T::BY - nbot + (ri - ntop);
+        } else {
+            const int e2 = e - n_rowpart, mi = e2 / cols_oob, cj = e2 - mi * cols_oob;
+            i = ntop + mi;
+            jj = cj < nleft ? cj : T::USED - nright + (cj - nleft);
+        }
+        int yy = dsc.oy + i, xx = dsc.ox + jj;
+        if (xx < 0 || xx > last_x) {
+            long long flat = static_cast<long long>(yy) * p.Wf + xx;
+            const long long last = static_cast<long long>(p.H) * p.Wf - 1;
+            flat = flat < 0 ? 0 : (flat > last ? last : flat);
+            const unsigned uf = static_cast<unsigned>(flat);
+            yy = static_cast<int>(uf / static_cast<unsigned>(p.Wf));
+            xx = static_cast<int>(uf - static_cast<unsigned>(yy) * static_cast<unsigned>(p.Wf));
+        } else if (yy < 0) {
+            yy = 0; xx = 0;
+        } else if (yy > last_y) {
+            yy = last_y; xx = last_x;
+        }
+        tile[T::off(i, (d + jj) >> 4) + ((d + jj) & 15)] = f[static_cast<long long>(yy) * p.pitch + xx];
+    }
+}
+
 // ----------------------------------------------------------------------------------------
 // the kernel
 // ----------------------------------------------------------------------------------------
@@ -567,7 +611,11 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                 dsc.pair = w.pair;
                 dsc.r0 = w.r0;
                 dsc.c0 = w.c0;
-                dsc.d = interior ? (dsc.ox & 15) : -1;
+                // partly outside (but the TMA box still overlaps the frame): TMA + patch of the outside elements;
+                // entirely outside, or no TMA: every element is gathered
+                const bool partial = p.use_tma && !interior && dsc.ox + T::USED > 0 && dsc.ox < p.Wf &&
+                                     dsc.oy + T::BY > 0 && dsc.oy < p.H;
+                dsc.d = interior ? (dsc.ox & 15) : (partial ? ((dsc.ox & 15) | kPatchFlag) : -1);
                 desc[q] = dsc;
             }
             __syncwarp();
@@ -575,6 +623,7 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
     };
 
     // ---- bring the tiles of `frame` into the (currently dead) window buffers ----------------
+    auto tile_ptr_plain = [&](int w2) -> unsigned char* { return smem + S::REG_OFF + w2 * G::REGION; };
     auto stage_issue = [&](int frame) {
         if constexpr (T::kFrame) {
             TileDesc* desc = reinterpret_cast<TileDesc*>(smem + S::TD_OFF);
@@ -650,6 +699,15 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
             if (s == 0 || s == 2) {
                 const int frame = s >> 1;
                 stage_wait(frame);
+                if constexpr (LOADER == LD_FRAME_INT || LOADER == LD_FRAME_CWS) {
+                    const TileDesc* desc = reinterpret_cast<const TileDesc*>(smem + S::TD_OFF);
+#pragma unroll 1
+                    for (int w2 = 0; w2 < NW; ++w2) {
+                        const TileDesc dsc = desc[w2 * 2 + frame];
+                        if (dsc.d >= kPatchFlag) patch_border_tile<W, LOADER>(p, dsc, tile_ptr_plain(w2), frame, lane);
+                    }
+                    __syncwarp();
+                }
                 if constexpr (kTC) {
                     // rows l and l + W/2 of this warp's window -> fp16 rows 32 q + l of the group's two operand
                     // tiles (q = this warp's TMEM lane quarter), so that after the MMAs lane l of THIS warp finds
@@ -706,7 +764,7 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                     tmem_wait_ld();
                 } else if constexpr (LOADER == LD_FRAME_INT || LOADER == LD_FRAME_ALN) {
                     const TileDesc* desc = reinterpret_cast<const TileDesc*>(smem + S::TD_OFF);
-                    const int d = desc[wi * 2 + frame].d;
+                    const int d = desc[wi * 2 + frame].d & 15;
                     uint32_t w0[W / 4], w1[W / 4];
                     // (a uniform switch over the word part of d with statically addressed registers instead
                     // of the select network was measured: no gain -- the loader is latency, not issue bound)
@@ -749,9 +807,9 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                     const int ra = 2 * l;
                     const AxisTap cyA = cws_axis(dsc.r0 + ra, dsc.vy), cyB = cws_axis(dsc.r0 + ra + 1, dsc.vy);
                     uint32_t wA[W / 4 + 1], wB[W / 4 + 1], wC[W / 4 + 1];
-                    load_row_words<W, LOADER, W / 4 + 1>(region, ra, dsc.d, wA);
-                    load_row_words<W, LOADER, W / 4 + 1>(region, ra + 1, dsc.d, wB);
-                    load_row_words<W, LOADER, W / 4 + 1>(region, ra + 2, dsc.d, wC);
+                    load_row_words<W, LOADER, W / 4 + 1>(region, ra, dsc.d & 15, wA);
+                    load_row_words<W, LOADER, W / 4 + 1>(region, ra + 1, dsc.d & 15, wB);
+                    load_row_words<W, LOADER, W / 4 + 1>(region, ra + 2, dsc.d & 15, wC);
                     float cA = u8f(wA[0], 0), cB = u8f(wB[0], 0), cC = u8f(wC[0], 0);
                     if (!anyflag) {
                         const float2 wy1 = make_float2(cyA.w1, cyB.w1), wy0 = make_float2(cyA.w0, cyB.w0);
