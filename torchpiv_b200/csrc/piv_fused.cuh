@@ -671,13 +671,16 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
     // warps in the same phase so that they share instruction fetches); a warp without work re-does
     // the last job with its output suppressed.
     if (p.sync_group && p.skew_ns > 0) __nanosleep(static_cast<unsigned>(p.skew_ns) * static_cast<unsigned>(warp >> 2));
+    bool prefetched = false;                   // frame a's tiles of this iteration's job are already in flight
 #pragma unroll 1
     for (int base = blockIdx.x * nwarps; base < njobs; base += job_stride) {
         const int job = min(base + warp, njobs - 1);
         const int g = min(job * NW + wi, n_total - 1);       // window of this lane (clamped: the last job may be ragged)
         const bool g_valid = (base + warp < njobs) && (job * NW + wi < n_total);
-        make_desc(job);
-        stage_issue(0);
+        if (!prefetched) {                     // otherwise the previous iteration's epilogue already did both
+            make_desc(job);
+            stage_issue(0);
+        }
 
         float sum_a = 0.f, sum_b = 0.f;        // pixel sums of the window (valid in lanes l == 0)
         float2 x[W];                           // the FFT operand
@@ -1086,12 +1089,48 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
             // lanes l == 0 hold the pixel sums of their window
             const float sa = __shfl_sync(FULL, sum_a, wi * HALF), sb = __shfl_sync(FULL, sum_b, wi * HALF);
             if (p.first_pass) eps *= (static_cast<double>(sa) / N2) * (static_cast<double>(sb) / N2);
+            const float f_l = at(il), f_r = at(ir), f_t = at(it_), f_b = at(ib);
+            // second peak: maximum outside the 7x7 flat-index patch around m, each patch index
+            // clamped to [0, N2-1] (PB:346-358).  Rows that cannot touch the patch reuse the
+            // row maxima from registers; the <= 8 candidate rows are rescanned from smem.
+            float sp = -FLT_MAX;
+            if (p.validate) {
+                const int lo_f = m - 3 - 3 * W, hi_f = m + 3 + 3 * W;
+                const int ra = max(lo_f, 0) >> LOGW, rb = min(hi_f, N2 - 1) >> LOGW;
+                if (l < ra || l > rb) sp = fmaxf(sp, mx_lo);
+                if (l + HALF < ra || l + HALF > rb) sp = fmaxf(sp, mx_hi);
+                for (int rr = ra; rr <= rb; ++rr) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int cc = l + h * HALF;
+                        const int f = rr * W + cc;
+                        const int e = f - lo_f;                     // (i+3) + W (j+3)
+                        bool in_patch = (e >= 0) && ((e & (W - 1)) <= 6) && ((e >> LOGW) <= 6);
+                        in_patch |= (f == 0 && lo_f <= 0) || (f == N2 - 1 && hi_f >= N2 - 1);
+                        if (!in_patch) sp = fmaxf(sp, mapw[rr * PC + cc]);
+                    }
+                }
+                sp = group_max<HALF>(sp);
+            }
+            // The map has been read for the last time: the next job's descriptors and frame-a tiles are requested
+            // now, so the TMA (and the shift loads of make_desc) run underneath the FP64 fit below.
+            // (Not for the CWS loader: measured 1-2 % slower there -- its descriptor set-up is heavier and the
+            // kernel is register-bound.)
+            if constexpr (LOADER != LD_FRAME_CWS) {
+                __syncwarp();
+                prefetched = false;
+                if (base + job_stride < njobs) {
+                    make_desc(min(base + job_stride + warp, njobs - 1));
+                    stage_issue(0);
+                    prefetched = true;
+                }
+            }
             const double dmin = static_cast<double>(gmin);
             const double cm = (static_cast<double>(gmax) - dmin) + eps;
-            const double cl = (static_cast<double>(at(il)) - dmin) + eps;
-            const double cr = (static_cast<double>(at(ir)) - dmin) + eps;
-            const double ct = (static_cast<double>(at(it_)) - dmin) + eps;
-            const double cb = (static_cast<double>(at(ib)) - dmin) + eps;
+            const double cl = (static_cast<double>(f_l) - dmin) + eps;
+            const double cr = (static_cast<double>(f_r) - dmin) + eps;
+            const double ct = (static_cast<double>(f_t) - dmin) + eps;
+            const double cb = (static_cast<double>(f_b) - dmin) + eps;
             // the five logarithms are evaluated by five lanes of the window (one log() body, 1/5 of the FP64 work)
             const double lsel = (l == 0) ? cm : (l == 1) ? cl : (l == 2) ? cr : (l == 3) ? ct : cb;
             const double lg = log(lsel);
@@ -1107,26 +1146,6 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
             bool invalid = false;
             float ratio = 0.f;
             if (p.validate) {
-                // second peak: maximum outside the 7x7 flat-index patch around m, each patch index
-                // clamped to [0, N2-1] (PB:346-358).  Rows that cannot touch the patch reuse the
-                // row maxima from registers; the <= 8 candidate rows are rescanned from smem.
-                const int lo_f = m - 3 - 3 * W, hi_f = m + 3 + 3 * W;
-                const int ra = max(lo_f, 0) >> LOGW, rb = min(hi_f, N2 - 1) >> LOGW;
-                float sp = -FLT_MAX;
-                if (l < ra || l > rb) sp = fmaxf(sp, mx_lo);
-                if (l + HALF < ra || l + HALF > rb) sp = fmaxf(sp, mx_hi);
-                for (int rr = ra; rr <= rb; ++rr) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int cc = l + h * HALF;
-                        const int f = rr * W + cc;
-                        const int e = f - lo_f;                     // (i+3) + W (j+3)
-                        bool in_patch = (e >= 0) && ((e & (W - 1)) <= 6) && ((e >> LOGW) <= 6);
-                        in_patch |= (f == 0 && lo_f <= 0) || (f == N2 - 1 && hi_f >= N2 - 1);
-                        if (!in_patch) sp = fmaxf(sp, mapw[rr * PC + cc]);
-                    }
-                }
-                sp = group_max<HALF>(sp);
                 const double c2 = (static_cast<double>(sp) - dmin) + eps;
                 const double rt = cm / c2;
                 invalid = rt < p.val_ratio;
