@@ -791,11 +791,7 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                         xw[e] = make_float4(cx.w1, cx.w1, cx.w0, cx.w0);      // pairs: operands of the packed taps
                         xf[e] = (cx.exact ? 2 : 0) | ((cx.lo - (dsc.ox + j)) & 1);
                         flag |= cx.exact;
-                        // rows: every row index appears as some j (square windows) -> same loop covers them
-                        const AxisTap cy = cws_axis(dsc.r0 + j, dsc.vy);
-                        flag |= cy.exact;
                     }
-                    const bool anyflag = __any_sync(FULL, flag);
                     __syncwarp();
                     const TileDesc dsc = desc[wi * 2 + frame];
                     const float4* xwq = xw + wi * W;
@@ -809,6 +805,9 @@ __global__ void __launch_bounds__(Smem<W, LOADER>::NWARPS * 32, 1) piv_fused_ker
                     // evaluation order).  5 packed FP32 instructions per output pair instead of 10 scalar ones.
                     const int ra = 2 * l;
                     const AxisTap cyA = cws_axis(dsc.r0 + ra, dsc.vy), cyB = cws_axis(dsc.r0 + ra + 1, dsc.vy);
+                    // exact-integer coordinates anywhere in the job (columns: the table loop above; rows: every row
+                    // of a window belongs to one of its lanes)
+                    const bool anyflag = __any_sync(FULL, flag || cyA.exact || cyB.exact);
                     uint32_t wA[W / 4 + 1], wB[W / 4 + 1], wC[W / 4 + 1];
                     load_row_words<W, LOADER, W / 4 + 1>(region, ra, dsc.d & 15, wA);
                     load_row_words<W, LOADER, W / 4 + 1>(region, ra + 1, dsc.d & 15, wB);
