@@ -1,17 +1,22 @@
-"""Import the UNMODIFIED reference backend (TEST INFRASTRUCTURE, this container only).
+"""Import the UNMODIFIED reference backend (TEST / BENCH INFRASTRUCTURE, never the product path).
 
-``/root/reference`` exists only in the build container, never on the GPU box, so this is
-used solely by ``tests/golden/make_golden.py`` (fixture generation) and by CPU tests that
-skip themselves when the reference is absent.  The reference package imports its Qt GUI
-at package import and ``imageio`` in the backend (unused); four empty stub modules are
-enough to load ``PIVbackend.py`` as is (recipe: SURVEY.md section 8c).
+Two places can hold it: ``baseline/_ref/torchPIV`` (pip-installed by ``baseline/install_ref.sh``;
+git-ignored, travels to the GPU box with the working tree) and ``/root/reference/src/torchPIV`` (build
+container only).  Users: ``tests/golden/make_golden.py`` (fixture generation), CPU tests that skip themselves
+when the reference is absent, and ``bench.py`` (``--impl reference`` and the torch-CUDA comparator leg).
+The reference package imports its Qt GUI at package import and ``imageio`` in the backend (unused); four
+empty stub modules are enough to load ``PIVbackend.py`` as is (recipe: SURVEY.md section 8c).
 """
 import importlib.util
 import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("TORCHPIV_REF", "/root/reference/src/torchPIV")
+_HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CANDIDATES = [os.environ.get("TORCHPIV_REF"), os.path.join(_HERE, "baseline", "_ref", "torchPIV"),
+               "/root/reference/src/torchPIV"]
+REF_ROOT = next((c for c in _CANDIDATES if c and os.path.isfile(os.path.join(c, "PIVbackend.py"))),
+                _CANDIDATES[-1])
 
 
 def available() -> bool:

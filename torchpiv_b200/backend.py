@@ -136,8 +136,9 @@ def correalte_fft(images_a: torch.Tensor, images_b: torch.Tensor) -> torch.Tenso
         code, a, b = 0, images_a.float().contiguous(), images_b.float().contiguous()
     c, w, _ = a.shape
     corr = torch.empty((c, w, w), dtype=torch.float32, device=dev)
-    _lib.check(_lib.lib().pivb200_correlate(a.data_ptr(), b.data_ptr(), code, c, w, corr.data_ptr(),
-                                            _stream(dev)))
+    with torch.cuda.device(dev):      # the C ABI launches on the CURRENT device
+        _lib.check(_lib.lib().pivb200_correlate(a.data_ptr(), b.data_ptr(), code, c, w, corr.data_ptr(),
+                                                _stream(dev)))
     return corr.to(out_dtype)
 
 
@@ -155,10 +156,11 @@ def correlation_to_displacement(corr: torch.Tensor, n_rows, n_cols, validate: bo
     u = torch.empty(c, dtype=torch.float64, device=dev)
     v = torch.empty(c, dtype=torch.float64, device=dev)
     m = torch.empty(c, dtype=torch.uint8, device=dev) if validate else None
-    _lib.check(_lib.lib().pivb200_corr_to_disp(
-        corr.data_ptr(), 0 if corr.dtype == torch.float32 else 1, c, d, k, 1 if validate else 0,
-        float(val_ratio), int(validation_window), u.data_ptr(), v.data_ptr(),
-        m.data_ptr() if validate else None, _stream(dev)))
+    with torch.cuda.device(dev):      # the C ABI launches on the CURRENT device
+        _lib.check(_lib.lib().pivb200_corr_to_disp(
+            corr.data_ptr(), 0 if corr.dtype == torch.float32 else 1, c, d, k, 1 if validate else 0,
+            float(val_ratio), int(validation_window), u.data_ptr(), v.data_ptr(),
+            m.data_ptr() if validate else None, _stream(dev)))
     mask = m.cpu().numpy().astype(bool).reshape(n_rows, n_cols) if validate else None
     return u.cpu().numpy().reshape(n_rows, n_cols), v.cpu().numpy().reshape(n_rows, n_cols), mask
 
@@ -176,9 +178,10 @@ def biliniar_interpolation_CWS(array: torch.Tensor, grid: torch.Tensor, vel_x: t
     vy = vel_y.to(dev, torch.float32).reshape(-1).contiguous()
     out = torch.empty(grid.shape, dtype=torch.float32, device=dev)
     epw = grid[0].numel()
-    _lib.check(_lib.lib().pivb200_bilinear_cws(frame.data_ptr(), frame.shape[-2], frame.shape[-1],
-                                               grid.data_ptr(), grid.numel(), epw, vx.data_ptr(),
-                                               vy.data_ptr(), out.data_ptr(), _stream(dev)))
+    with torch.cuda.device(dev):      # the C ABI launches on the CURRENT device
+        _lib.check(_lib.lib().pivb200_bilinear_cws(frame.data_ptr(), frame.shape[-2], frame.shape[-1],
+                                                   grid.data_ptr(), grid.numel(), epw, vx.data_ptr(),
+                                                   vy.data_ptr(), out.data_ptr(), _stream(dev)))
     return out
 
 
@@ -194,9 +197,10 @@ def interpolation_DWS(array: torch.Tensor, grid: torch.Tensor, vel_x: torch.Tens
     vy = vel_y.to(dev, torch.int64).reshape(-1).contiguous()
     out = torch.empty(grid.shape, dtype=torch.uint8, device=dev)
     epw = grid[0].numel()
-    _lib.check(_lib.lib().pivb200_shift_dws(frame.data_ptr(), frame.shape[-2], frame.shape[-1],
-                                            grid.data_ptr(), grid.numel(), epw, vx.data_ptr(),
-                                            vy.data_ptr(), out.data_ptr(), _stream(dev)))
+    with torch.cuda.device(dev):      # the C ABI launches on the CURRENT device
+        _lib.check(_lib.lib().pivb200_shift_dws(frame.data_ptr(), frame.shape[-2], frame.shape[-1],
+                                                grid.data_ptr(), grid.numel(), epw, vx.data_ptr(),
+                                                vy.data_ptr(), out.data_ptr(), _stream(dev)))
     return out
 
 
@@ -217,10 +221,11 @@ def extended_search_area_piv(frame_a, frame_b, window_size=32, overlap=0, valida
     u = torch.empty((n_rows, n_cols), dtype=torch.float64, device=dev)
     v = torch.empty_like(u)
     m = torch.empty((n_rows, n_cols), dtype=torch.uint8, device=dev) if validate else None
-    _lib.check(_lib.lib().pivb200_pass_first(
-        fa.data_ptr(), fb.data_ptr(), 1, 0, h, w, fa.stride(0), int(window_size), int(overlap),
-        1 if validate else 0, float(validation_ratio), u.data_ptr(), v.data_ptr(),
-        m.data_ptr() if validate else None, None, _stream(dev)))
+    with torch.cuda.device(dev):      # the C ABI launches on the CURRENT device
+        _lib.check(_lib.lib().pivb200_pass_first(
+            fa.data_ptr(), fb.data_ptr(), 1, 0, h, w, fa.stride(0), int(window_size), int(overlap),
+            1 if validate else 0, float(validation_ratio), u.data_ptr(), v.data_ptr(),
+            m.data_ptr() if validate else None, None, _stream(dev)))
     mask = m.cpu().numpy().astype(bool) if validate else None
     return u.cpu().numpy(), v.cpu().numpy(), x, y, mask
 
@@ -271,16 +276,18 @@ class _PivIteration:
         base_u, base_v, pred_u, pred_v, u, v = (torch.empty(n, dtype=f64, device=dev) for _ in range(6))
         m = torch.empty(n, dtype=torch.uint8, device=dev) if validate else None
         st = _stream(dev)
-        _lib.check(L.pivb200_predictor(up.data_ptr(), vp.data_ptr(), mp.data_ptr() if validate else None,
-                                       1, n0, m0, n1, m1, ay.data_ptr(), ax.data_ptr(), mode,
-                                       tmp.data_ptr(), sx.data_ptr(), sy.data_ptr(), base_u.data_ptr(),
-                                       base_v.data_ptr(), pred_u.data_ptr(), pred_v.data_ptr(), st))
+        with torch.cuda.device(dev):      # the C ABI launches on the CURRENT device
+            _lib.check(L.pivb200_predictor(up.data_ptr(), vp.data_ptr(), mp.data_ptr() if validate else None,
+                                           1, n0, m0, n1, m1, ay.data_ptr(), ax.data_ptr(), mode,
+                                           tmp.data_ptr(), sx.data_ptr(), sy.data_ptr(), base_u.data_ptr(),
+                                           base_v.data_ptr(), pred_u.data_ptr(), pred_v.data_ptr(), st))
         h, w = self.frame_shape
-        _lib.check(L.pivb200_pass_next(fa.data_ptr(), fb.data_ptr(), 1, 0, h, w, fa.stride(0),
-                                       self.wind_size, self.overlap, mode, sx.data_ptr(), sy.data_ptr(),
-                                       base_u.data_ptr(), base_v.data_ptr(), pred_u.data_ptr(),
-                                       pred_v.data_ptr(), 1 if validate else 0, 1.2, u.data_ptr(),
-                                       v.data_ptr(), m.data_ptr() if validate else None, None, st))
+        with torch.cuda.device(dev):      # the C ABI launches on the CURRENT device
+            _lib.check(L.pivb200_pass_next(fa.data_ptr(), fb.data_ptr(), 1, 0, h, w, fa.stride(0),
+                                           self.wind_size, self.overlap, mode, sx.data_ptr(), sy.data_ptr(),
+                                           base_u.data_ptr(), base_v.data_ptr(), pred_u.data_ptr(),
+                                           pred_v.data_ptr(), 1 if validate else 0, 1.2, u.data_ptr(),
+                                           v.data_ptr(), m.data_ptr() if validate else None, None, st))
         val = m.cpu().numpy().astype(bool).reshape(n1, m1) if validate else None
         return (u.cpu().numpy().reshape(n1, m1), v.cpu().numpy().reshape(n1, m1), self.x, self.y, val)
 

@@ -356,6 +356,10 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float2 (&v)[8]) {
         "f"(v[7].y)
         : "memory");
 }
+// one pair = 2 columns
+__device__ __forceinline__ void tmem_st_pair(uint32_t taddr, float2 v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "f"(v.x), "f"(v.y) : "memory");
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float2 (&v)[8]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"

@@ -1,0 +1,594 @@
+// Fused PIV pass kernel, pair-packed variant (32 px and 16 px windows, displacement sink) for sm_100a.
+//
+// Same job as piv_fused_kernel (window extraction by TMA -> CWS / DWS window shift -> 2-D cross-correlation
+// -> fft-shifted peak search, sub-pixel fit, peak-ratio validation, predictor glue; PB:147-257, 346-422,
+// 728-738 / 800-810) and the same decomposition -- persistent CTAs, a warp owns a job of 64 / W windows,
+// H = W/2 lanes per window -- but every lane runs H-point transforms on PAIRS (fft_soa.cuh,
+// piv_soa_math.cuh) instead of one W-point transform on (re, im)-packed registers:
+//
+//   R   lane l transforms window rows (2l, 2l+1) as the pair: real rows -> H-point complex FFT + split
+//       step -> quads (re pair, im pair) X [row pair l][column c] in shared memory (STS.128)
+//   C   lane c reads column c (LDS.128): the pair is (even rows, odd rows); H-point FFT + radix-2 step
+//       across the pair -> (Y[q], Y[q+H]).  Frame a's spectrum is PARKED in tensor memory (lane-private
+//       scratch: tcgen05.st / ld) while frame b goes through R and C
+//   P   conj(A^) B^ (packed); column 0 (= the two real columns 0 and W/2) is separated with the help of
+//       the other lanes through a scratch area, as in piv_fused_kernel
+//   C'  radix-2 step across the pair, inverse H-point FFT -> quads Q [row pair m][column c]
+//   R'  lane l reads the half spectra of rows (2l, 2l+1), inverse real transform -> two rows of the map
+//   E   epilogue: min / first-max / flat neighbours / second peak / FP64 fit on the fft-shifted map
+//
+// Versus piv_fused_kernel<32, ...>: all FFT arithmetic is packed FADD2 / FMUL2 / FFMA2 with immediate
+// twiddles (the radix-2 steps across a pair are the only scalar FP32 work), every exchange is a 128-bit
+// shared-memory access (a third of the LDS / STS instructions), the per-lane state is 64 data registers
+// for a 16-point pair transform instead of a 32-point transform plus its temporaries, so 20 warps are
+// resident instead of 16 with no spills, and the code (~25 KB) fits the instruction cache without the
+// shared run-time FFT body.
+#pragma once
+#include "piv_fused.cuh"
+#include "piv_soa_math.cuh"
+
+namespace pivb200 {
+
+template <int W>
+struct GeoS {
+    static_assert(W == 16 || W == 32 || W == 64, "window size");
+    static constexpr int NW = 64 / W;                 // windows per warp job
+    static constexpr int H = W / 2;                   // lanes per window = transform length
+    static constexpr int LOGW = (W == 64) ? 6 : ((W == 32) ? 5 : 4);
+    static constexpr int PQ = H + 1;                  // pitch of X / Q rows in pairs (8 B); odd -> conflict free
+    static constexpr int PLANE = H * PQ;              // pairs per plane: real parts first, imaginary parts behind them
+    static constexpr int XB = 2 * PLANE * 8;
+    static constexpr int PM = W + 1;                  // pitch of a map row PAIR in float2
+    static constexpr int MAPB = H * PM * 8;
+    static constexpr int SCRB = 6 * H * 8;            // column-0 scratch: (re, im) pair arrays of the a, b spectra and of V
+    // the windows of a warp keep their data at staggered offsets so that scalar accesses of different windows
+    // hit different banks; 128-bit accesses are issued per quarter warp = per window anyway
+    static constexpr int STAGGER = 64 * (NW - 1);
+    __host__ __device__ static constexpr int doff(int wi) { return wi * 64; }
+    static constexpr int MAXB = XB > MAPB ? (XB > SCRB ? XB : SCRB) : (MAPB > SCRB ? MAPB : SCRB);
+    static constexpr int REGION = ((MAXB + STAGGER + 255) / 256) * 256;
+    static constexpr float K = 4.0f * W * W;          // map = K * sum_x a(x) b(x+s)
+    static constexpr int TCOLS = 2 * W;               // TMEM columns one warp parks (H elements x 4 words)
+};
+
+// NROWS consecutive tile rows starting at `row0`, each realigned to start at byte `d` (0..15) of the staged row.
+// The word part of d is the same for all lanes of a window, so a switch over statically indexed registers
+// (uniform per half / quarter warp) replaces the two-level select network of load_row_words; the byte part is one
+// funnel shift per word.
+template <int W, int LOADER, int NROWS, int NOUT>
+__device__ __forceinline__ void load_rows_realigned(const unsigned char* tile, int row0, int d, uint32_t (&out)[NROWS][NOUT]) {
+    using T = Tile<W, LOADER>;
+    constexpr int NL = T::BX / 4;
+    static_assert(NOUT + 3 <= NL + 1, "one zero word pads the row");
+    uint32_t L[NROWS][NL + 1];
+    static_for<0, NROWS>([&](auto rc) {
+        constexpr int r = decltype(rc)::value;
+        static_for<0, T::BX / 16>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            const uint4 q = *reinterpret_cast<const uint4*>(tile + T::off(row0 + r, c));
+            L[r][4 * c] = q.x; L[r][4 * c + 1] = q.y; L[r][4 * c + 2] = q.z; L[r][4 * c + 3] = q.w;
+        });
+        L[r][NL] = 0u;
+    });
+    const int sh = (d & 3) * 8;
+    auto realign = [&](auto sc) {
+        constexpr int s = decltype(sc)::value;
+        static_for<0, NROWS>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            static_for<0, NOUT>([&](auto kc) {
+                constexpr int k = decltype(kc)::value;
+                out[r][k] = __funnelshift_r(L[r][k + s], L[r][k + s + 1], sh);
+            });
+        });
+    };
+    switch (d >> 2) {
+        case 0: realign(std::integral_constant<int, 0>{}); break;
+        case 1: realign(std::integral_constant<int, 1>{}); break;
+        case 2: realign(std::integral_constant<int, 2>{}); break;
+        default: realign(std::integral_constant<int, 3>{}); break;
+    }
+}
+
+template <int W, int LOADER>
+struct SmemS {
+    using G = GeoS<W>;
+    using T = Tile<W, LOADER>;
+    static_assert(LOADER == LD_FRAME_INT || LOADER == LD_FRAME_CWS || LOADER == LD_FRAME_ALN, "frame loaders only");
+    static_assert(T::TX <= G::REGION, "the tile is staged inside the window's buffer");
+    static constexpr int REG_OFF = 0;
+    static constexpr int XW_OFF = REG_OFF + G::NW * G::REGION;               // float4 [NW][W]  (CWS column taps, each weight twice)
+    static constexpr int XW = (LOADER == LD_FRAME_CWS) ? G::NW * W * 16 : 0;
+    static constexpr int XF_OFF = XW_OFF + XW;                               // int    [NW][W]
+    static constexpr int XF = (LOADER == LD_FRAME_CWS) ? G::NW * W * 4 : 0;
+    static constexpr int TD_OFF = ((XF_OFF + XF + 15) / 16) * 16;            // TileDesc [NW][2]
+    static constexpr int TD = G::NW * 2 * 32;
+    static constexpr int BAR_OFF = ((TD_OFF + TD + 7) / 8) * 8;
+    static constexpr int TOTAL = BAR_OFF + 8;
+    static constexpr int STRIDE = ((TOTAL + T::BASE_ALIGN - 1) / T::BASE_ALIGN) * T::BASE_ALIGN;
+    static constexpr int SMEM_MAX = 232448 - 1024;
+#ifndef PIVB200_S32_WARPS
+#define PIVB200_S32_WARPS 20
+#endif
+#ifndef PIVB200_S16_WARPS
+#define PIVB200_S16_WARPS 28
+#endif
+#ifndef PIVB200_S64_WARPS
+#define PIVB200_S64_WARPS 12
+#endif
+    static constexpr int WARP_CAP = (W == 64) ? PIVB200_S64_WARPS : ((W == 32) ? PIVB200_S32_WARPS : PIVB200_S16_WARPS);
+    static constexpr int TMEM_CAP = 4 * (512 / G::TCOLS);
+    static constexpr int BY_SMEM = SMEM_MAX / STRIDE;
+    static constexpr int NWARPS0 = BY_SMEM < WARP_CAP ? BY_SMEM : WARP_CAP;
+    static constexpr int NWARPS = NWARPS0 < TMEM_CAP ? NWARPS0 : TMEM_CAP;
+    static constexpr int CTA_BYTES = NWARPS * STRIDE;
+};
+
+template <int W, int LOADER>
+__global__ void __launch_bounds__(SmemS<W, LOADER>::NWARPS * 32, 1) piv_soa_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                        const __grid_constant__ CUtensorMap tmB,
+                                                        const __grid_constant__ PassParams p) {
+    using G = GeoS<W>;
+    using T = Tile<W, LOADER>;
+    using S = SmemS<W, LOADER>;
+    using M = SoaMath<W>;
+    constexpr int NW = G::NW, H = G::H, LOGW = G::LOGW, PQ = G::PQ, PM = G::PM;
+    constexpr unsigned FULL = 0xffffffffu;
+
+    extern __shared__ __align__(1024) unsigned char smem_cta[];
+    __shared__ uint32_t tmem_base_sh;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    unsigned char* smem = smem_cta + warp * S::STRIDE;
+    const int n_total = static_cast<int>(p.n_total);
+    const int njobs = (n_total + NW - 1) / NW;
+    const int job_stride = gridDim.x * nwarps;
+    const uint32_t bar = smem_u32(smem + S::BAR_OFF);
+
+    if (warp == 0) tmem_alloc_512(smem_u32(&tmem_base_sh));
+    tmem_fence_before();
+    __syncthreads();
+    tmem_fence_after();
+    // parking area of this warp: its 32 lanes, TCOLS columns per group of four warps
+    const uint32_t tpark = tmem_base_sh + (static_cast<uint32_t>((warp & 3) * 32) << 16) +
+                           static_cast<uint32_t>((warp >> 2) * G::TCOLS);
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+
+    const int wi = lane / H;               // window of this lane inside the job
+    const int l = lane % H;                // row pair l in phases R and R', column l in phases C and C'
+    unsigned char* const region = smem + S::REG_OFF + wi * G::REGION;
+    // X / Q of this lane's window: plane of real pairs [H][PQ], plane of imaginary pairs behind it.  (Two 64-bit
+    // accesses per element instead of one 128-bit access: a quad would need the two pairs in four consecutive
+    // registers, which costs four MOVs per element -- measured, profiles/r02a.)
+    float2* const Xr = reinterpret_cast<float2*>(region + G::doff(wi));
+    float2* const Xi = Xr + G::PLANE;
+
+    auto make_desc = [&](int job) {
+        TileDesc* desc = reinterpret_cast<TileDesc*>(smem + S::TD_OFF);
+        if (lane < NW * 2) {
+            const int q = lane, frame = q & 1;
+            const int g = min(job * NW + (q >> 1), n_total - 1);
+            const WinGeo w = window_geo(p, g);
+            TileDesc dsc;
+            frame_origin<LOADER>(p, g, w, frame, dsc.oy, dsc.ox, dsc.vy, dsc.vx);
+            const bool interior = p.use_tma && dsc.ox >= 0 && dsc.oy >= 0 &&
+                                  dsc.ox + T::USED <= p.Wf && dsc.oy + T::BY <= p.H;
+            dsc.pair = w.pair;
+            dsc.r0 = w.r0;
+            dsc.c0 = w.c0;
+            const bool partial = p.use_tma && !interior && dsc.ox + T::USED > 0 && dsc.ox < p.Wf &&
+                                 dsc.oy + T::BY > 0 && dsc.oy < p.H;
+            dsc.d = interior ? (dsc.ox & 15) : (partial ? ((dsc.ox & 15) | kPatchFlag) : -1);
+            desc[q] = dsc;
+        }
+        __syncwarp();
+    };
+    auto stage_issue = [&](int frame) {
+        TileDesc* desc = reinterpret_cast<TileDesc*>(smem + S::TD_OFF);
+        fence_proxy_async();            // generic accesses to the buffers are ordered before the TMA writes
+        __syncwarp();
+        uint32_t tx = 0;
+#pragma unroll 1
+        for (int w2 = 0; w2 < NW; ++w2) {
+            const TileDesc dsc = desc[w2 * 2 + frame];
+            if (dsc.d >= 0) tx += T::TX;
+            else gather_border_tile<W, LOADER>(p, dsc, smem + S::REG_OFF + w2 * G::REGION, frame, lane);
+        }
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar, tx);      // armed for every (job, frame): the parity at the wait is `frame`
+#pragma unroll 1
+            for (int w2 = 0; w2 < NW; ++w2) {
+                const TileDesc dsc = desc[w2 * 2 + frame];
+                if (dsc.d >= 0) {
+                    const uint32_t dst = smem_u32(smem + S::REG_OFF + w2 * G::REGION);
+                    if (frame) tma_load_3d(dst, &tmB, bar, dsc.ox & ~15, dsc.oy, dsc.pair);
+                    else tma_load_3d(dst, &tmA, bar, dsc.ox & ~15, dsc.oy, dsc.pair);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane < NW && desc[lane * 2 + frame].d < 0) desc[lane * 2 + frame].d = 0;     // gathered tiles start at byte 0
+        __syncwarp();
+    };
+
+    // optional lock step (instruction-fetch sharing): bit i of p.sync_mask puts a named barrier over groups of
+    // p.sync_group warps at phase boundary i (0 rows, 1 columns, 2 product, 3 inverse columns, 4 inverse rows, 5 epilogue)
+    auto lockstep = [&](int point) {
+        if ((p.sync_mask >> point) & 1) {
+            // sync_group == 0: the warps of one scheduler (warp & 3) form a group -- they share the scheduler's L0
+            // instruction cache; otherwise groups of sync_group consecutive warps
+            if (p.sync_group == 0) asm volatile("bar.sync %0, %1;" ::"r"(1 + (warp & 3)), "r"((nwarps >> 2) * 32) : "memory");
+            else asm volatile("bar.sync %0, %1;" ::"r"(1 + warp / p.sync_group), "r"(p.sync_group * 32) : "memory");
+        }
+    };
+    bool prefetched = false;
+#pragma unroll 1
+    for (int base = blockIdx.x * nwarps; base < njobs; base += job_stride) {
+        const int job = min(base + warp, njobs - 1);
+        const int g = min(job * NW + wi, n_total - 1);
+        const bool g_valid = (base + warp < njobs) && (job * NW + wi < n_total);
+        if (!prefetched) {
+            make_desc(job);
+            stage_issue(0);
+        }
+
+        float sum_a = 0.f, sum_b = 0.f;        // pixel sums of the window (valid in lanes l == 0)
+        float2 x[W];
+#pragma unroll 1
+        for (int frame = 0; frame < 2; ++frame) {
+            // ------------------------------------------------------------- tiles -> rows (2l, 2l+1) in x[j]
+            lockstep(0);
+            mbar_wait(bar, static_cast<uint32_t>(frame));
+            const TileDesc* desc = reinterpret_cast<const TileDesc*>(smem + S::TD_OFF);
+            if constexpr (LOADER == LD_FRAME_INT || LOADER == LD_FRAME_CWS) {
+#pragma unroll 1
+                for (int w2 = 0; w2 < NW; ++w2) {
+                    const TileDesc dsc = desc[w2 * 2 + frame];
+                    if (dsc.d >= kPatchFlag)
+                        patch_border_tile<W, LOADER>(p, dsc, smem + S::REG_OFF + w2 * G::REGION, frame, lane);
+                }
+                __syncwarp();
+            }
+            if constexpr (LOADER == LD_FRAME_INT || LOADER == LD_FRAME_ALN) {
+                const int d = desc[wi * 2 + frame].d & 15;
+                uint32_t w[2][W / 4];
+                if constexpr (LOADER == LD_FRAME_ALN) {
+                    load_row_words<W, LOADER, W / 4>(region, 2 * l, d, w[0]);
+                    load_row_words<W, LOADER, W / 4>(region, 2 * l + 1, d, w[1]);
+                } else {
+                    load_rows_realigned<W, LOADER, 2, W / 4>(region, 2 * l, d, w);
+                }
+                static_for<0, W>([&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    x[j] = make_float2(u8f(w[0][j >> 2], j & 3), u8f(w[1][j >> 2], j & 3));
+                });
+            } else {
+                float4* xw = reinterpret_cast<float4*>(smem + S::XW_OFF);
+                int* xf = reinterpret_cast<int*>(smem + S::XF_OFF);
+                // per-column tap descriptors of this frame (shared by all rows of a window)
+                bool flag = false;
+#pragma unroll
+                for (int e = lane; e < NW * W; e += 32) {
+                    const int j = e & (W - 1), w2 = e >> LOGW;
+                    const TileDesc dsc = desc[w2 * 2 + frame];
+                    const AxisTap cx = cws_axis(dsc.c0 + j, dsc.vx);
+                    xw[e] = make_float4(cx.w1, cx.w1, cx.w0, cx.w0);      // pairs: operands of the packed taps
+                    xf[e] = (cx.exact ? 2 : 0) | ((cx.lo - (dsc.ox + j)) & 1);
+                    flag |= cx.exact;
+                }
+                __syncwarp();
+                const TileDesc dsc = desc[wi * 2 + frame];
+                const float4* xwq = xw + wi * W;
+                const int* xfq = xf + wi * W;
+                // Window rows (2l, 2l+1) need tile rows 2l .. 2l+2.  The reference's four-term sum (PB:187-192) is
+                // evaluated in separable form, vertical tap first (piv_fused.cuh has the derivation); the result IS
+                // the pair (row 2l, row 2l+1) the row transform wants.
+                const int ra = 2 * l;
+                const AxisTap cyA = cws_axis(dsc.r0 + ra, dsc.vy), cyB = cws_axis(dsc.r0 + ra + 1, dsc.vy);
+                const bool anyflag = __any_sync(FULL, flag || cyA.exact || cyB.exact);
+                uint32_t wABC[3][W / 4 + 1];
+                load_rows_realigned<W, LOADER, 3, W / 4 + 1>(region, ra, dsc.d & 15, wABC);
+                const uint32_t (&wA)[W / 4 + 1] = wABC[0], (&wB)[W / 4 + 1] = wABC[1], (&wC)[W / 4 + 1] = wABC[2];
+                float cA = u8f(wA[0], 0), cB = u8f(wB[0], 0), cC = u8f(wC[0], 0);
+                if (!anyflag) {
+                    const float2 wy1 = make_float2(cyA.w1, cyB.w1), wy0 = make_float2(cyA.w0, cyB.w0);
+                    float2 vc = pfma(make_float2(cA, cB), wy1, pmul(make_float2(cB, cC), wy0));
+                    static_for<0, W>([&](auto jc) {
+                        constexpr int j = decltype(jc)::value;
+                        const float nA = u8f(wA[(j + 1) >> 2], (j + 1) & 3);
+                        const float nB = u8f(wB[(j + 1) >> 2], (j + 1) & 3);
+                        const float nC = u8f(wC[(j + 1) >> 2], (j + 1) & 3);
+                        const float2 vn = pfma(make_float2(nA, nB), wy1, pmul(make_float2(nB, nC), wy0));
+                        const float4 wx = xwq[j];
+                        x[j] = pfma(vc, make_float2(wx.x, wx.y), pmul(vn, make_float2(wx.z, wx.w)));
+                        vc = vn;
+                    });
+                } else {
+                    // some coordinate of the job is an exact integer: there the reference's weights all vanish and
+                    // the value is patched to the tap at (floor y, floor x) (PB:170, 193)
+                    const bool jyA = (cyA.lo - (dsc.oy + ra)) & 1, jyB = (cyB.lo - (dsc.oy + ra + 1)) & 1;
+                    static_for<0, W>([&](auto jc) {
+                        constexpr int j = decltype(jc)::value;
+                        const float nA = u8f(wA[(j + 1) >> 2], (j + 1) & 3);
+                        const float nB = u8f(wB[(j + 1) >> 2], (j + 1) & 3);
+                        const float nC = u8f(wC[(j + 1) >> 2], (j + 1) & 3);
+                        const float4 wx4 = xwq[j];
+                        const float2 wx = make_float2(wx4.x, wx4.z);
+                        const int fl = xfq[j];
+                        const float hA = fmaf(cA, wx.x, nA * wx.y);
+                        const float hB = fmaf(cB, wx.x, nB * wx.y);
+                        const float hC = fmaf(cC, wx.x, nC * wx.y);
+                        const float qA = (fl & 1) ? nA : cA, qB = (fl & 1) ? nB : cB, qC = (fl & 1) ? nC : cC;
+                        const float vA = ((fl & 2) || cyA.exact) ? (jyA ? qB : qA) : fmaf(hA, cyA.w1, hB * cyA.w0);
+                        const float vB = ((fl & 2) || cyB.exact) ? (jyB ? qC : qB) : fmaf(hB, cyB.w1, hC * cyB.w0);
+                        x[j] = make_float2(vA, vB);
+                        cA = nA; cB = nB; cC = nC;
+                    });
+                }
+            }
+            __syncwarp();                       // tiles fully read before X overwrites the buffer
+
+            // ------------------------------------------------------------- R: rows -> X
+            M::row_forward(x);
+            static_for<0, H>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                constexpr int e = M::pos(c);
+                Xr[l * PQ + c] = x[2 * e];
+                Xi[l * PQ + c] = x[2 * e + 1];
+            });
+            __syncwarp();
+            // ------------------------------------------------------------- C: column l
+            lockstep(1);
+            static_for<0, H>([&](auto tc) {
+                constexpr int t = decltype(tc)::value;
+                x[2 * t] = Xr[t * PQ + l];
+                x[2 * t + 1] = Xi[t * PQ + l];
+            });
+            __syncwarp();                       // X fully read: the buffer is dead
+            if (frame == 0) stage_issue(1);     // frame b's tiles arrive while column a is transformed
+            M::col_forward(x);
+            if (frame == 0) {
+                // one pair per store: a wider store wants its registers consecutive (MOVs)
+                static_for<0, W>([&](auto ic) { constexpr int i = decltype(ic)::value; tmem_st_pair(tpark + 2 * i, x[i]); });
+                tmem_wait_st();
+            }
+        }
+
+        // ------------------------------------------------------------- P: conj(A^) B^
+        lockstep(2);
+        {
+            // Column 0 is the packed pair of real columns (bins 0 and W/2): C = c0^ + i cH^.  Its lane drops both
+            // spectra into a scratch area AS PAIRS (element q = bins (q, q+H), real pairs and imaginary pairs in
+            // separate arrays: no register shuffling), the H lanes of the window do the H + 1 small separation
+            // jobs in parallel, and the lane reads the packed product back.
+            float2* const sBr = Xr;                 // [H] each
+            float2* const sBi = Xr + H;
+            float2* const sAr = Xr + 2 * H;
+            float2* const sAi = Xr + 3 * H;
+            float2* const sVr = Xr + 4 * H;
+            float2* const sVi = Xr + 5 * H;
+            if (l == 0) {
+                static_for<0, H>([&](auto qc) {
+                    constexpr int q = decltype(qc)::value;
+                    constexpr int e = M::pos(q);
+                    sBr[q] = x[2 * e];
+                    sBi[q] = x[2 * e + 1];
+                });
+            }
+            static_for<0, W / 8>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;             // 4 elements = 8 pairs = 16 columns
+                float2 A[8];
+                tmem_ld8(tpark + 16 * c, A);
+                tmem_wait_ld();
+                if (l == 0) {
+                    static_for<0, 4>([&](auto ic) {
+                        constexpr int i = decltype(ic)::value;
+                        constexpr int q = M::posinv(4 * c + i);             // element 4c + i holds bins (q, q+H)
+                        sAr[q] = A[2 * i];
+                        sAi[q] = A[2 * i + 1];
+                    });
+                }
+                static_for<0, 4>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    constexpr int e = 4 * c + i;
+                    const float2 ar = A[2 * i], ai = A[2 * i + 1], br = x[2 * e], bi = x[2 * e + 1];
+                    x[2 * e] = pfma(ar, br, pmul(ai, bi));
+                    x[2 * e + 1] = pfma(ar, bi, pneg(pmul(ai, br)));
+                });
+            });
+            __syncwarp();
+            {
+                // bin q of a spectrum: component q & 1... no: element q % H, half q / H
+                const float* fAr = reinterpret_cast<const float*>(sAr), *fAi = reinterpret_cast<const float*>(sAi);
+                const float* fBr = reinterpret_cast<const float*>(sBr), *fBi = reinterpret_cast<const float*>(sBi);
+                float* fVr = reinterpret_cast<float*>(sVr), *fVi = reinterpret_cast<float*>(sVi);
+                // lane l > 0: bins q = l (element l, half 0) and W - l (element H - l, half 1); lane 0: bins 0 and H
+                const int iq = (l == 0) ? 0 : 2 * l, in = (l == 0) ? 1 : 2 * (H - l) + 1;
+                const float2 Aq = make_float2(fAr[iq], fAi[iq]), An = make_float2(fAr[in], fAi[in]);
+                const float2 Bq = make_float2(fBr[iq], fBi[iq]), Bn = make_float2(fBr[in], fBi[in]);
+                float2 Vq, Vn;
+                if (l == 0) {
+                    // bins 0 and W/2 are their own partners: everything is real
+                    sum_a = 0.5f * Aq.x;
+                    sum_b = 0.5f * Bq.x;
+                    // the DC bin (mean product) is dropped: a constant that `- amin` removes anyway
+                    Vq = make_float2(0.f, Aq.y * Bq.y);
+                    Vn = make_float2(An.x * Bn.x, An.y * Bn.y);
+                } else {
+                    const float2 a0 = make_float2(Aq.x + An.x, Aq.y - An.y);      // 2 c0^[q]
+                    const float2 ah = make_float2(Aq.y + An.y, An.x - Aq.x);      // 2 cH^[q]
+                    const float2 b0 = make_float2(0.25f * (Bq.x + Bn.x), 0.25f * (Bq.y - Bn.y));
+                    const float2 bh = make_float2(0.25f * (Bq.y + Bn.y), 0.25f * (Bn.x - Bq.x));
+                    const float2 P0 = make_float2(fmaf(a0.x, b0.x, a0.y * b0.y), fmaf(a0.x, b0.y, -a0.y * b0.x));
+                    const float2 Ph = make_float2(fmaf(ah.x, bh.x, ah.y * bh.y), fmaf(ah.x, bh.y, -ah.y * bh.x));
+                    // V[q] = P0 + i Ph, V[W-q] = conj(P0) + i conj(Ph)
+                    Vq = make_float2(P0.x - Ph.y, P0.y + Ph.x);
+                    Vn = make_float2(P0.x + Ph.y, Ph.x - P0.y);
+                }
+                fVr[iq] = Vq.x; fVi[iq] = Vq.y;
+                fVr[in] = Vn.x; fVi[in] = Vn.y;
+            }
+            __syncwarp();
+            if (l == 0) {
+                static_for<0, H>([&](auto qc) {
+                    constexpr int q = decltype(qc)::value;
+                    constexpr int e = M::pos(q);
+                    x[2 * e] = sVr[q];
+                    x[2 * e + 1] = sVi[q];
+                });
+            }
+            __syncwarp();                       // scratch fully read before Q overwrites the buffer
+        }
+
+        // ------------------------------------------------------------- C': inverse column -> Q
+        lockstep(3);
+        M::col_inverse(x);
+        static_for<0, H>([&](auto mc) {
+            constexpr int m = decltype(mc)::value;
+            constexpr int e = M::pos2(m);
+            Xr[m * PQ + l] = x[2 * e];
+            Xi[m * PQ + l] = x[2 * e + 1];
+        });
+        __syncwarp();
+        // ------------------------------------------------------------- R': rows (2l, 2l+1) of the map
+        lockstep(4);
+        static_for<0, H>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            x[2 * c] = Xr[l * PQ + c];
+            x[2 * c + 1] = Xi[l * PQ + c];
+        });
+        __syncwarp();                           // Q fully read before the map overwrites it
+        M::row_inverse(x);
+
+        // raw rows (2l, 2l+1) -> rows (sr0, sr0 + 1) of the fft-shifted map, a row PAIR per float2:
+        // element (R, C) of the shifted map lives at float index ((R >> 1) * PM + C) * 2 + (R & 1)
+        float* const mapw = reinterpret_cast<float*>(Xr);
+        float2* const mapw2 = Xr;
+        const int sr0 = (2 * l + H) & (W - 1);
+        float mx0 = -FLT_MAX, mx1 = -FLT_MAX, mn = FLT_MAX;
+        static_for<0, W>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            constexpr int sc = (j + H) % W;
+            const float2 o = x[2 * M::pos(j >> 1) + (j & 1)];
+            mapw2[(sr0 >> 1) * PM + sc] = o;
+            mx0 = fmaxf(mx0, o.x);
+            mx1 = fmaxf(mx1, o.y);
+            mn = fminf(mn, fminf(o.x, o.y));
+        });
+        __syncwarp();
+
+        // =============================== epilogue (PB:360-422, 728-738) ==========================
+        lockstep(5);
+        {
+            auto at2 = [&](int R, int C) { return mapw[((R >> 1) * PM + C) * 2 + (R & 1)]; };
+            double base_u = 0.0, base_v = 0.0, pred_u = 0.0, pred_v = 0.0;
+            if (l == 0 && g_valid) {
+                if (p.base_u) { base_u = p.base_u[g]; base_v = p.base_v[g]; }
+                if (p.pred_u) { pred_u = p.pred_u[g]; pred_v = p.pred_v[g]; }
+            }
+            const float gmax = group_max<H>(fmaxf(mx0, mx1)), gmin = group_min<H>(mn);
+            // first maximum in flat (row-major) order of the shifted map (torch argmax, PB:383)
+            constexpr int BIG = 1 << 20;
+            int R = group_min_int<H>(min(mx0 == gmax ? sr0 : BIG, mx1 == gmax ? sr0 + 1 : BIG));
+            R = min(R, W - 1);      // only reachable with NaN input
+            int C = group_min_int<H>((at2(R, l) == gmax) ? l : ((at2(R, l + H) == gmax) ? l + H : BIG));
+            C = min(C, W - 1);
+            constexpr int N2 = W * W;
+            const int m = R * W + C;
+            auto at = [&](int f) { return at2(f >> LOGW, f & (W - 1)); };
+            // flat neighbours, guarded only at the array ends (PB:385-392)
+            const int il = (m + 1 >= N2 - 1) ? m : m + 1;
+            const int ir = (m - 1 <= 0) ? m : m - 1;
+            const int it_ = (m + W >= N2 - 1) ? m : m + W;
+            const int ib = (m - W <= 0) ? m : m - W;
+            double eps = static_cast<double>(G::K) * 1e-7;
+            const float sa = __shfl_sync(FULL, sum_a, wi * H), sb = __shfl_sync(FULL, sum_b, wi * H);
+            if (p.first_pass) eps *= (static_cast<double>(sa) / N2) * (static_cast<double>(sb) / N2);
+            const float f_l = at(il), f_r = at(ir), f_t = at(it_), f_b = at(ib);
+            // second peak: maximum outside the 7x7 flat-index patch around m, each patch index clamped to
+            // [0, N2-1] (PB:346-358).  Rows that cannot touch the patch reuse the row maxima from registers.
+            float sp = -FLT_MAX;
+            if (p.validate) {
+                const int lo_f = m - 3 - 3 * W, hi_f = m + 3 + 3 * W;
+                const int ra = max(lo_f, 0) >> LOGW, rb = min(hi_f, N2 - 1) >> LOGW;
+                if (sr0 < ra || sr0 > rb) sp = fmaxf(sp, mx0);
+                if (sr0 + 1 < ra || sr0 + 1 > rb) sp = fmaxf(sp, mx1);
+                for (int rr = ra; rr <= rb; ++rr) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int cc = l + h * H;
+                        const int f = rr * W + cc;
+                        const int e = f - lo_f;                     // (i+3) + W (j+3)
+                        bool in_patch = (e >= 0) && ((e & (W - 1)) <= 6) && ((e >> LOGW) <= 6);
+                        in_patch |= (f == 0 && lo_f <= 0) || (f == N2 - 1 && hi_f >= N2 - 1);
+                        if (!in_patch) sp = fmaxf(sp, at2(rr, cc));
+                    }
+                }
+                sp = group_max<H>(sp);
+            }
+            // The map has been read for the last time: the next job's descriptors and frame-a tiles are requested
+            // now, so the TMA runs underneath the FP64 fit below.
+            __syncwarp();
+            prefetched = false;
+            if (base + job_stride < njobs) {
+                make_desc(min(base + job_stride + warp, njobs - 1));
+                stage_issue(0);
+                prefetched = true;
+            }
+            const double dmin = static_cast<double>(gmin);
+            const double cm = (static_cast<double>(gmax) - dmin) + eps;
+            const double cl = (static_cast<double>(f_l) - dmin) + eps;
+            const double cr = (static_cast<double>(f_r) - dmin) + eps;
+            const double ct = (static_cast<double>(f_t) - dmin) + eps;
+            const double cb = (static_cast<double>(f_b) - dmin) + eps;
+            // the five logarithms are evaluated by five lanes of the window (one log() body, 1/5 of the FP64 work)
+            const double lsel = (l == 0) ? cm : (l == 1) ? cl : (l == 2) ? cr : (l == 3) ? ct : cb;
+            const double lg = log(lsel);
+            const int l0 = wi * H;
+            const double lm = __shfl_sync(FULL, lg, l0), ll = __shfl_sync(FULL, lg, l0 + 1), lr = __shfl_sync(FULL, lg, l0 + 2),
+                         lt = __shfl_sync(FULL, lg, l0 + 3), lb = __shfl_sync(FULL, lg, l0 + 4);
+            double du = static_cast<double>(C) + (lr - ll) / (2.0 * (ll + lr) - 4.0 * lm) - static_cast<double>(H);
+            double dv = static_cast<double>(R) + (lb - lt) / (2.0 * (lb + lt) - 4.0 * lm) - static_cast<double>(H);
+            // torch.nan_to_num (PB:418-419)
+            du = isnan(du) ? 0.0 : (isinf(du) ? copysign(DBL_MAX, du) : du);
+            dv = isnan(dv) ? 0.0 : (isinf(dv) ? copysign(DBL_MAX, dv) : dv);
+
+            bool invalid = false;
+            float ratio = 0.f;
+            if (p.validate) {
+                const double c2 = (static_cast<double>(sp) - dmin) + eps;
+                const double rt = cm / c2;
+                invalid = rt < p.val_ratio;
+                ratio = static_cast<float>(rt);
+            }
+            if (p.first_pass && (sa == 0.f || sb == 0.f)) {
+                // black window: the reference divides by a zero mean (PB:513-514), every value is NaN,
+                // nan_to_num gives 0 and the NaN ratio compares False (valid)
+                du = dv = 0.0;
+                invalid = false;
+                ratio = 0.f;
+            }
+            if (l == 0 && g_valid) {
+                double uo = du + base_u;
+                double vo = dv + base_v;
+                if (p.pred_u) {
+                    // PB:731-738: reject where the correction exceeds a positive predictor, or invalid
+                    if ((du > pred_u && rint(pred_u) > 0.0) || invalid) uo = pred_u;
+                    if ((dv > pred_v && rint(pred_v) > 0.0) || invalid) vo = pred_v;
+                }
+                p.u[g] = uo;
+                p.v[g] = vo;
+                if (p.mask) p.mask[g] = invalid ? 1 : 0;
+                if (p.ratio) p.ratio[g] = ratio;
+            }
+            __syncwarp();
+        }
+    }
+
+    tmem_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc_512(tmem_base_sh);
+}
+
+}  // namespace pivb200

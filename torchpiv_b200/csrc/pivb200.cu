@@ -13,6 +13,7 @@
 
 #include "../../include/pivb200.h"
 #include "fused_launch.cuh"
+#include "soa_launch.cuh"
 #include "piv_params.h"
 
 namespace pivb200 {
@@ -85,6 +86,15 @@ static int check_geometry(int H, int W, int pitch, int wind, int overlap, int n_
 
 static int launch_fused(int wind, int loader, int sink, const CUtensorMap& ta, const CUtensorMap& tb,
                         const PassParams& p, cudaStream_t s) {
+    // 32 / 16 px displacement passes run the pair-packed kernels (piv_soa.cuh); PIVB200_SOA=0 keeps the
+    // one-transform-per-lane kernels (piv_fused.cuh) for A/B measurements
+    static const bool soa = [] { const char* e = getenv("PIVB200_SOA"); return !(e && e[0] == '0'); }();
+    if (soa && sink == SK_DISP && (loader == LD_FRAME_INT || loader == LD_FRAME_ALN || loader == LD_FRAME_CWS)) {
+        static const bool soa64 = [] { const char* e = getenv("PIVB200_SOA64"); return e && e[0] == '1'; }();
+        if (wind == 64 && soa64) return launch_soa_w64(loader, ta, tb, p, s);
+        if (wind == 32) return launch_soa_w32(loader, ta, tb, p, s);
+        if (wind == 16) return launch_soa_w16(loader, ta, tb, p, s);
+    }
     switch (wind) {
         case 64: return launch_fused_w64(loader, sink, ta, tb, p, s);
         case 32: return launch_fused_w32(loader, sink, ta, tb, p, s);

@@ -129,6 +129,11 @@ class PIVPlan:
             frames_a, frames_b = frames_a[None], frames_b[None]
         self._check_frames(frames_a, frames_b)
         B = frames_a.shape[0]
+        # the C ABI launches on the CURRENT device: make it the plan's for the duration of the call
+        with torch.cuda.device(self.device):
+            return self._run(frames_a, frames_b, B, stream, validate)
+
+    def _run(self, frames_a, frames_b, B, stream, validate):
         ws = self._workspace(B)
         L = self.lib
         if stream is None:

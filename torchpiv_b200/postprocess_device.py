@@ -65,9 +65,10 @@ def normalized_median_test(u: torch.Tensor, v: torch.Tensor, mask: Optional[torc
         out = torch.empty(u.shape, dtype=torch.uint8, device=u.device)
     else:
         _check_mask(out, u)
-    _lib.check(_lib.lib().pivb200_nmt(u.data_ptr(), v.data_ptr(), mask.data_ptr() if mask is not None else None,
-                                      B, n_rows, n_cols, float(threshold), float(eps), out.data_ptr(),
-                                      _stream(u.device, stream)))
+    with torch.cuda.device(u.device):      # the C ABI launches on the CURRENT device
+        _lib.check(_lib.lib().pivb200_nmt(u.data_ptr(), v.data_ptr(), mask.data_ptr() if mask is not None else None,
+                                          B, n_rows, n_cols, float(threshold), float(eps), out.data_ptr(),
+                                          _stream(u.device, stream)))
     return out
 
 
@@ -88,8 +89,9 @@ def replace_invalid(u: torch.Tensor, v: torch.Tensor, invalid: torch.Tensor, max
         max_sweeps = max(n_rows, n_cols)
     if workspace is None:
         workspace = replace_workspace(u)
-    _lib.check(_lib.lib().pivb200_replace(u.data_ptr(), v.data_ptr(), invalid.data_ptr(), B, n_rows, n_cols,
-                                          int(max_sweeps), workspace.data_ptr(), _stream(u.device, stream)))
+    with torch.cuda.device(u.device):      # the C ABI launches on the CURRENT device
+        _lib.check(_lib.lib().pivb200_replace(u.data_ptr(), v.data_ptr(), invalid.data_ptr(), B, n_rows, n_cols,
+                                              int(max_sweeps), workspace.data_ptr(), _stream(u.device, stream)))
 
 
 class StencilPost:
@@ -163,6 +165,9 @@ class FieldStatistics:
         self.n_rows, self.n_cols = int(n_rows), int(n_cols)
         # mean u, mean v, then centred second-moment sums uu, vv, uv (merged batch by batch on the device)
         self.moments_dev = torch.zeros((5, self.n_rows, self.n_cols), dtype=torch.float64, device=self.device)
+        # the zero fill runs on the current stream, add() may run on another (non-blocking) one: order them
+        self._zeroed = torch.cuda.Event()
+        self._zeroed.record(torch.cuda.current_stream(self.device))
         self.count = 0
 
     def add(self, u, v, stream=None) -> None:
@@ -175,8 +180,13 @@ class FieldStatistics:
         B, n_rows, n_cols = _check_fields(u, v)
         if (n_rows, n_cols) != (self.n_rows, self.n_cols):
             raise ValueError("field shape does not match the accumulator")
-        _lib.check(_lib.lib().pivb200_stats_accumulate(u.data_ptr(), v.data_ptr(), B, n_rows, n_cols, self.count,
-                                                       self.moments_dev.data_ptr(), _stream(self.device, stream)))
+        if self._zeroed is not None:
+            # first use: `stream` is a raw handle (or None = current stream) -- a one-off host wait is the simplest order
+            self._zeroed.synchronize()
+            self._zeroed = None
+        with torch.cuda.device(self.device):      # the C ABI launches on the CURRENT device
+            _lib.check(_lib.lib().pivb200_stats_accumulate(u.data_ptr(), v.data_ptr(), B, n_rows, n_cols, self.count,
+                                                           self.moments_dev.data_ptr(), _stream(self.device, stream)))
         self.count += B
 
     def state(self):
