@@ -4,26 +4,28 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A "step" is one pass of the hot path (pass 1 at 64/32 + predictor + CWS pass 2 at 32/16) over
-one batch of PAIRS_PER_STEP synthetic 2048x2048 particle-image pairs per GPU.
+A "step" is one pass of the hot path (pass 1 at 64/32 + predictor + CWS pass 2 at 32/16) over 16 batches of 32
+synthetic 2048x2048 particle-image pairs per GPU (512 pairs; 20 steps last about a second).
 
-  value : whole-job pairs/s with the frames already resident in HBM (CUDA events on the launch
-          stream, barrier + synchronize on both sides, max over ranks).  The batch (2 x 32 x 4 MB
-          = 268 MB of frames) is larger than the 126 MB L2, so every step re-reads it from HBM.
-  e2e   : the same metric through the public host API (HostPipeline: pinned host frames -> H2D ->
-          fused kernels -> D2H of u, v, mask), copies inside the timed region every step.
+  value : whole-job pairs/s with the frames already resident in HBM (CUDA events on the launch stream, barrier +
+          synchronize on both sides, max over ranks).  A batch (2 x 32 x 4 MB = 268 MB of frames) is larger than
+          the 126 MB L2, so every launch re-reads it from HBM.
+  e2e   : the same metric through the public host API (HostPipeline: pinned host frames -> H2D -> fused kernels
+          -> D2H of u, v, mask), copies inside the timed region for every batch; next to it the ceiling a plain
+          pinned cudaMemcpyAsync of the same buffers reaches in the same run (all ranks at once).
+  e2e_files : BASELINE config 5 -- a sequential-mode folder of bmp files through OfflinePIV(...)(), sharded over
+          the ranks, reference-exact hole filling and the device stencil.
   roofline     : dominant kernel (CWS pass at 32 px) against the FFMA peak measured in this run.
-  cpu_baseline : the CPU oracle (NumPy/SciPy port of the reference path, all host threads) on a
-                 bounded sample of the same workload, rank 0 only.
-  torch_eager_baseline : the same chain restated with stock eager PyTorch ops on the same GPU
-                 (oracle/torch_eager.py), bounded sample, rank 0 only -- the "torch-CUDA path" comparator.
+  cpu_baseline : the UNMODIFIED reference (baseline/_ref) with device=cpu on the host cores, bounded sample,
+                 rank 0 only (kind "reference"; the NumPy oracle port, kind "port", when baseline/_ref is absent).
+  torch_eager_baseline : the UNMODIFIED reference with device=cuda on the same GPU (its own torch-CUDA path),
+                 bounded sample, rank 0 only -- the comparator north_star names.
 
-Multi-GPU (torchrun, one rank per GPU): pairs are independent, so each rank processes its own
-shard of pairs (weak scaling); torch.distributed is used for the barrier and the max-over-ranks
-of the device time only -- there is no collective on the data path.
+Multi-GPU (torchrun, one rank per GPU): pairs are independent, so each rank processes its own shard of pairs
+(weak scaling); torch.distributed is used for the barrier and the max-over-ranks of the device time only --
+there is no collective on the data path.
 
---impl reference times the reference's own algorithm on the host cores (the CPU oracle; the
-reference is pure Python/PyTorch and cannot travel to the GPU box -- see DESIGN.md).
+--impl reference times the reference's own CPU path (baseline/_ref, device=cpu, all host threads).
 """
 import argparse
 import json
@@ -255,12 +257,53 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def files_leg(T, synth, dev, rank, world, n_pairs_total, decode_threads, fill_workers):
+    """BASELINE config 5: a sequential-mode folder of 4 MP bmp files through the public generator
+    OfflinePIV(...)() (decode threads -> pinned staging -> H2D -> fused passes -> D2H -> host post-processing),
+    sharded by pair index over the ranks (shard=(rank, world), no collective).  K unique frames are written once
+    and hard-linked cyclically, so every file is decoded while the disk footprint stays small.  Returns
+    {mode: (pairs done by this rank, seconds)} for the reference-exact hole filling and the device stencil."""
+    import shutil
+    import tempfile
+    K = 16
+    tmp = tempfile.mkdtemp(prefix=f"pivfiles_r{rank}_")
+    out = {}
+    try:
+        noise, blank = synth.default_patches(SHAPE)
+        a, b = synth.particle_pair(SHAPE, synth.uniform_shift(3.3, -2.2), seed=7, noise_patch=noise, blank_patch=blank)
+        uniq = []
+        for k in range(K):
+            fr = np.roll(a if k % 2 == 0 else b, (7 * (k // 2), 11 * (k // 2)), axis=(0, 1))
+            path = os.path.join(tmp, f"uniq{k}.bin")
+            synth.write_bmp(path, fr)
+            uniq.append(path)
+        folder = os.path.join(tmp, "seq")
+        os.makedirs(folder)
+        for i in range(n_pairs_total + 1):
+            os.link(uniq[i % K], os.path.join(folder, f"frame{i:05d}.bmp"))
+        for mode, kw in (("reference", dict(replace="reference", fill_workers=fill_workers)),
+                         ("stencil", dict(replace="stencil"))):
+            piv = T.OfflinePIV(folder=folder, device=f"cuda:{dev.index}", file_fmt="bmp", wind_size=WIND, overlap=OVERLAP,
+                               multipass=PASSES, multipass_mode=MODE, multipass_scale=SCALE, dt=12, scale=0.02,
+                               folder_mode="sequential", batch_pairs=32, decode_threads=decode_threads,
+                               shard=(rank, world), **kw)
+            n = 0
+            t0 = time.perf_counter()
+            for _ in piv():
+                n += 1
+            out[mode] = (n, len(piv), time.perf_counter() - t0)
+            piv.close()
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import torchpiv_b200 as T
-    from torchpiv_b200 import _lib
-    from torchpiv_b200.engine import HostPipeline
+    from torchpiv_b200 import _lib, synth
+    from torchpiv_b200.engine import FramePipeline, HostPipeline
 
     rank, world, local = dist_env()
     if not torch.cuda.is_available():
@@ -275,14 +318,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def max_over_ranks(ms: float) -> float:
+    def reduce(x: float, op) -> float:
         if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    B = args.pairs_per_step
+    def max_over_ranks(ms: float) -> float:
+        return reduce(ms, dist.ReduceOp.MAX) if world > 1 else ms
+
+    B, R = args.pairs_per_batch, args.batches_per_step
     # ---- synthetic data: a few rendered pairs, rolled into B distinct pairs per rank -----------
     base = make_pairs(UNIQUE_PAIRS, seed0=1000 * rank)
     host_a = torch.empty((B,) + SHAPE, dtype=torch.uint8).pin_memory()
@@ -297,7 +343,7 @@ def run_ours(args):
     plan = T.PIVPlan(SHAPE, WIND, OVERLAP, PASSES, MODE, SCALE, device=dev)
     stream = torch.cuda.current_stream(dev)
 
-    # ---- device-resident timing -----------------------------------------------------------------
+    # ---- device-resident timing: a step = R batches of B pairs (the timed region lasts ~1 s) -----
     for _ in range(max(args.warmup, 3)):
         plan.run(fa, fb)
     barrier()
@@ -308,14 +354,14 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(args.steps * R):
         plan.run(fa, fb)
     e1.record(stream)
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    value = world * B * args.steps / (ms_total * 1e-3)
+    value = world * B * R * args.steps / (ms_total * 1e-3)
 
     # sanity: the benchmarked computation produced the imposed displacement
     u, v, m = plan.run(fa[:1], fb[:1])
@@ -324,7 +370,26 @@ def run_ours(args):
     if abs(med_u - 3.3) > 0.1 or abs(med_v + 2.2) > 0.1:
         raise SystemExit(f"benchmark output is wrong: median displacement {med_u:.3f}, {med_v:.3f}")
 
-    # ---- end to end through the host API --------------------------------------------------------
+    # ---- plain pinned H2D copies, all ranks at once: the ceiling of the end-to-end number ---------------
+    cstream = torch.cuda.Stream(dev)
+    dst = torch.empty_like(fa)
+    with torch.cuda.stream(cstream):
+        dst.copy_(host_a, non_blocking=True)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_copy = 8
+    with torch.cuda.stream(cstream):
+        c0.record(cstream)
+        for i in range(n_copy):
+            dst.copy_(host_a if i % 2 == 0 else host_b, non_blocking=True)
+        c1.record(cstream)
+    cstream.synchronize()
+    barrier()
+    copy_ms = max_over_ranks(c0.elapsed_time(c1))
+    h2d_ceiling_gbs = world * n_copy * host_a.numel() / (copy_ms * 1e-3) / 1e9
+    del dst
+
+    # ---- end to end through the host API: every batch pays its H2D and D2H -------------------------------
     pipe = HostPipeline(plan, B)
     for _ in range(2):
         pipe.result(pipe.submit(host_a, host_b))
@@ -333,7 +398,7 @@ def run_ours(args):
     t0 = time.perf_counter()
     pending = None
     checksum = 0.0
-    for _ in range(args.steps):
+    for _ in range(args.steps * R):
         sid = pipe.submit(host_a, host_b)
         if pending is not None:
             ru, rv, rm = pipe.result(pending)
@@ -344,13 +409,12 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_ms = max_over_ranks(e2e_s * 1e3)
-    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+    e2e_value = world * B * R * args.steps / (e2e_ms * 1e-3)
     h2d_step = (pipe.h2d_bytes - h0) // args.steps
     d2h_step = (pipe.d2h_bytes - d0) // args.steps
+    e2e_h2d_gbs = world * h2d_step * args.steps / (e2e_ms * 1e-3) / 1e9
 
-    # ---- the same, sequential-folder style (BASELINE config 5): pair i = frames (i, i+1), so a batch of
-    # B pairs uploads B + 1 frames instead of 2 B (the kernels read two overlapping views of one stack) ----
-    from torchpiv_b200.engine import FramePipeline
+    # ---- the same, sequential-folder style: pair i = frames (i, i+1), a batch of B pairs uploads B + 1 frames ----
     del pipe
     fpipe = FramePipeline(plan, B)
     for sid in (0, 1):
@@ -362,9 +426,10 @@ def run_ours(args):
         fpipe.result(sid)
     barrier()
     sh0 = fpipe.h2d_bytes
+    seq_batches = max(args.steps * R // 4, 4)
     t0 = time.perf_counter()
     prev = None
-    for i in range(args.steps):
+    for i in range(seq_batches):
         fpipe.submit(i & 1, B, chained=True)
         if prev is not None:
             checksum += float(fpipe.result(prev)[0][0, 0, 0])
@@ -372,8 +437,29 @@ def run_ours(args):
     checksum += float(fpipe.result(prev)[0][0, 0, 0])
     barrier()
     seq_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
-    seq_value = world * B * args.steps / (seq_ms * 1e-3)
-    seq_h2d_step = (fpipe.h2d_bytes - sh0) // args.steps
+    seq_value = world * B * seq_batches / (seq_ms * 1e-3)
+    seq_h2d_batch = (fpipe.h2d_bytes - sh0) // seq_batches
+    del fpipe
+
+    # ---- BASELINE config 5: the sequential batch FROM FILES through OfflinePIV, sharded over the ranks ----------
+    files = None
+    if args.files_pairs > 0:
+        cores = os.cpu_count() or 1
+        per_rank = max(1, cores // world)
+        decode_threads = max(2, min(8, per_rank // 2))
+        fill_workers = max(1, per_rank - decode_threads)
+        barrier()
+        t0 = time.perf_counter()
+        res = files_leg(T, synth, dev, rank, world, args.files_pairs, decode_threads, fill_workers)
+        files = {}
+        for mode, (n_yield, n_pairs, secs) in res.items():
+            t_max = max_over_ranks(secs * 1e3) * 1e-3
+            tot = reduce(float(n_pairs), dist.ReduceOp.SUM) if world > 1 else float(n_pairs)
+            files[mode] = {"value": tot / t_max, "unit": "pairs/s", "pairs": int(tot), "seconds": t_max,
+                           "yielded_rank0": n_yield}
+        files["config"] = {"files": args.files_pairs + 1, "folder_mode": "sequential", "unique_frames": 16,
+                           "decode_threads_per_rank": decode_threads, "fill_workers_per_rank": fill_workers,
+                           "host_cores": cores, "api": "torchpiv_b200.OfflinePIV(...)() with shard=(rank, world)"}
 
     if rank != 0:
         if world > 1:
@@ -420,12 +506,14 @@ def run_ours(args):
     flops_first = B * geo[0][2] * flops_per_window(geo[0][0])
     flops_next = B * geo[1][2] * flops_per_window(geo[1][0])
     achieved = flops_next / (ms_next * 1e-3) / 1e12
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tpath):
         try:
-            traffic = json.load(open(tpath)).get("pass_next_cws_w32_dram_bytes_per_pair")
+            tj = json.load(open(tpath))
+            traffic = tj.get("pass_next_cws_w32_dram_bytes_per_pair")
             traffic = traffic * B if traffic is not None else None
+            traffic_src = tj.get("source")
         except (OSError, ValueError):
             traffic = None
     peaks = {}
@@ -434,61 +522,79 @@ def run_ours(args):
         peaks = json.load(open(ppath))
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     bytes_next = B * (2 * SHAPE[0] * SHAPE[1] + 18 * geo[1][2])
-    roofline = {"bound": "fp32", "kernel": "piv_fused_kernel<32, CWS, DISP> (pass 2)", "achieved": achieved,
+    ms_step = ms_total / (args.steps * R)            # one batch of B pairs
+    roofline = {"bound": "fp32", "kernel": "piv_soa_kernel<32, CWS> (pass 2)", "achieved": achieved,
                 "peak": peak.value, "peak_source": "FFMA micro-benchmark run by this bench.py (MEASURED_PEAKS.json has no FP32 figure)",
-                "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": traffic,
+                "unit": "TFLOP/s", "frac": achieved / peak.value, "traffic": traffic, "traffic_source": traffic_src,
                 "ms_per_launch": ms_next, "algorithmic_flops_per_launch": flops_next,
-                "share_of_step": ms_next / (ms_total / args.steps),
-                "pass_first": {"ms_per_launch": ms_first, "achieved": flops_first / (ms_first * 1e-3) / 1e12,
+                "share_of_step": ms_next / ms_step,
+                "pass_first": {"kernel": "piv_soa_kernel<64, ALN> (pass 1)", "ms_per_launch": ms_first,
+                               "achieved": flops_first / (ms_first * 1e-3) / 1e12,
                                "frac": flops_first / (ms_first * 1e-3) / 1e12 / peak.value},
-                "whole_step_frac": (flops_first + flops_next) / (ms_total / args.steps * 1e-3) / 1e12 / peak.value,
+                "whole_step_frac": (flops_first + flops_next) / (ms_step * 1e-3) / 1e12 / peak.value,
                 "hbm": {"achieved": bytes_next / (ms_next * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": bytes_next / (ms_next * 1e-3) / 1e9 / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"}}
 
-    # ---- CPU baseline (bounded sample) ----------------------------------------------------------
+    # ---- CPU baseline (bounded sample): the reference on the host cores --------------------------
     cores = os.cpu_count() or 1
     n_cpu = args.cpu_pairs
-    cpu_rate, cpu_dt = cpu_oracle_rate(n_cpu, warmup=1)
-    # ---- stock eager PyTorch on the same GPU (restatement of the reference's op chain, bounded sample) ----
-    torch_eager = None
+    cpu_rate, cpu_dt, cpu_kind, cpu_what = cpu_reference_rate(n_cpu, warmup=1)
+    # ---- the reference's own torch-CUDA path on this GPU (bounded sample) -------------------------
+    torch_cuda = None
     if args.torch_pairs > 0:
-        from oracle import torch_eager as E
-        second = E.IterCWS(SHAPE, WIND // 2, OVERLAP // 2, dev)
-        E.two_pass_cws(fa[0], fb[0], WIND, OVERLAP, second)              # warm-up (cuFFT plans, allocator)
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        for i in range(args.torch_pairs):
-            E.two_pass_cws(fa[i % B], fb[i % B], WIND, OVERLAP, second)
-        torch.cuda.synchronize(dev)
-        te = time.perf_counter() - t0
-        torch_eager = {"value": args.torch_pairs / te, "unit": "pairs/s", "kind": "port",
-                       "what": "oracle/torch_eager.py: the reference's op chain restated with stock eager PyTorch "
-                               "(aten + cuFFT kernels, 3 D2H syncs and host SciPy splines per pass) on this GPU, "
-                               "frames resident; the reference's own sources cannot travel to the GPU box",
-                       "sample": f"{args.torch_pairs} 4MP pairs, 2-pass CWS, {te:.2f} s"}
-        del second
+        PB = load_reference()
+        if PB is not None:
+            rate, te = reference_pass_rate(PB, dev, [(host_a[i].numpy(), host_b[i].numpy()) for i in range(4)],
+                                           args.torch_pairs, warmup=3)
+            key = next((k for k, d in PB.DeviceMap.devicies.items() if d == dev or str(d) == str(dev)), None)
+            off_rate, off_n = (reference_offline_rate(PB, key, 12, 2) if key is not None else (None, 0))
+            torch_cuda = {"value": rate, "unit": "pairs/s", "kind": "reference",
+                          "what": "UNMODIFIED reference (baseline/_ref) on this GPU: extended_search_area_piv + "
+                                  "piv_iteration_CWS.__call__ (PB:874-882) with device=cuda, frames resident",
+                          "sample": f"{args.torch_pairs} 4MP pairs after 3 warm-up pairs, 2-pass CWS, {te:.2f} s",
+                          "offline_piv_from_files": {"value": off_rate, "unit": "pairs/s", "pairs": off_n,
+                                                     "what": "reference OfflinePIV(...)() generator from bmp files "
+                                                             "(decode, H2D, passes, host hole filling), device=cuda"}}
+        else:
+            from oracle import torch_eager as E
+            second = E.IterCWS(SHAPE, WIND // 2, OVERLAP // 2, dev)
+            E.two_pass_cws(fa[0], fb[0], WIND, OVERLAP, second)              # warm-up (cuFFT plans, allocator)
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            for i in range(args.torch_pairs):
+                E.two_pass_cws(fa[i % B], fb[i % B], WIND, OVERLAP, second)
+            torch.cuda.synchronize(dev)
+            te = time.perf_counter() - t0
+            torch_cuda = {"value": args.torch_pairs / te, "unit": "pairs/s", "kind": "port",
+                          "what": "oracle/torch_eager.py (restatement with stock eager PyTorch); baseline/_ref is absent",
+                          "sample": f"{args.torch_pairs} 4MP pairs, 2-pass CWS, {te:.2f} s"}
+            del second
         torch.cuda.empty_cache()
 
     line = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": B, "frame_bytes_per_step_per_gpu": 2 * B * SHAPE[0] * SHAPE[1],
-                   "l2_policy": "inputs larger than L2 (268 MB of frames per step vs 126 MB L2)",
+        "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": B * R, "batches_per_step": R, "pairs_per_batch": B,
+                   "frame_bytes_per_batch_per_gpu": 2 * B * SHAPE[0] * SHAPE[1],
+                   "l2_policy": "inputs larger than L2 (268 MB of frames per batch vs 126 MB L2)",
                    "sharding": "pairs split across ranks, no data-path collective"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d_step),
                 "d2h_bytes_per_step": int(d2h_step), "ms_per_step": e2e_ms / args.steps,
+                "h2d_gbs": e2e_h2d_gbs, "h2d_ceiling_gbs": h2d_ceiling_gbs,
+                "h2d_ceiling_what": "plain pinned cudaMemcpyAsync of the same buffers, all ranks at once, measured in this run",
                 "api": "torchpiv_b200.engine.HostPipeline (pinned host frames in, u/v/mask on the host out)"},
-        "e2e_sequential": {"value": seq_value, "unit": "pairs/s", "h2d_bytes_per_step": int(seq_h2d_step),
-                           "ms_per_step": seq_ms / args.steps,
+        "e2e_sequential": {"value": seq_value, "unit": "pairs/s", "h2d_bytes_per_batch": int(seq_h2d_batch),
+                           "batches": seq_batches,
                            "note": "informative: sequential-folder pairing (pair i = frames i, i+1), every frame "
                                    "uploaded once; same kernels, torchpiv_b200.engine.FramePipeline"},
-        "gpu_launches": int(launches), "launches_per_step": plan.launches_per_batch,
+        "e2e_files": files,
+        "gpu_launches": int(launches), "launches_per_batch": plan.launches_per_batch,
         "clocks": clocks, "roofline": roofline,
-        "cpu_baseline": {"value": cpu_rate, "unit": "pairs/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_cpu} 4MP pairs, 2-pass CWS pass functions (CPU oracle, scipy.fft workers=-1), {cpu_dt:.1f} s"},
-        "torch_eager_baseline": torch_eager,
+        "cpu_baseline": {"value": cpu_rate, "unit": "pairs/s", "cores": cores, "kind": cpu_kind,
+                         "sample": f"{n_cpu} 4MP pairs, 2-pass CWS pass functions, {cpu_dt:.1f} s; {cpu_what}"},
+        "torch_eager_baseline": torch_cuda,
         "check": {"median_u_px": med_u, "median_v_px": med_v, "imposed": [3.3, -2.2]},
     }
     print(json.dumps(line))
@@ -499,13 +605,17 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs-per-step", type=int, default=PAIRS_PER_STEP)
-    ap.add_argument("--cpu-pairs", type=int, default=4, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--pairs-per-batch", type=int, default=PAIRS_PER_STEP, help="pairs per kernel launch (per GPU)")
+    ap.add_argument("--batches-per-step", type=int, default=16,
+                    help="batches per step: a step is 16 x 32 = 512 pairs per GPU, so that 20 steps last ~1 s")
+    ap.add_argument("--cpu-pairs", type=int, default=3, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--torch-pairs", type=int, default=24,
-                    help="size of the bounded eager-PyTorch-on-GPU sample (0 = skip)")
+                    help="size of the bounded reference-on-GPU sample (0 = skip)")
+    ap.add_argument("--files-pairs", type=int, default=2048,
+                    help="pairs of the from-files leg (BASELINE config 5; 4000 = the full configuration, 0 = skip)")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: re-launch under torchrun, one rank per GPU

@@ -78,20 +78,20 @@ static double run_case(unsigned seed, bool drop_dc) {
                     xb[2 * e + 1] = make_float2(sV[q].y, sV[q + H].y);
                 }
             }
-            M::col_inverse(xb);
+            M::col_inverse(xb);                    // result swapped: real pair in the odd slot
             for (int m = 0; m < H; ++m) {
-                Q[2 * (m * H + c)] = xb[2 * M::pos2(m)];
-                Q[2 * (m * H + c) + 1] = xb[2 * M::pos2(m) + 1];
+                Q[2 * (m * H + c)] = xb[2 * M::pos(m) + 1];
+                Q[2 * (m * H + c) + 1] = xb[2 * M::pos(m)];
             }
         }
     }
     std::vector<double> got(W * W);
     for (int l = 0; l < H; ++l) {
         float2 x[W];
-        for (int c = 0; c < H; ++c) { x[2 * c] = Q[2 * (l * H + c)]; x[2 * c + 1] = Q[2 * (l * H + c) + 1]; }
+        for (int c = 0; c < H; ++c) { x[2 * c + 1] = Q[2 * (l * H + c)]; x[2 * c] = Q[2 * (l * H + c) + 1]; }   // swapped
         M::row_inverse(x);
         for (int m = 0; m < H; ++m) {
-            const float2 ev = x[2 * M::pos(m)], od = x[2 * M::pos(m) + 1];
+            const float2 ev = x[2 * M::pos(m) + 1], od = x[2 * M::pos(m)];
             got[(2 * l) * W + 2 * m] = ev.x; got[(2 * l + 1) * W + 2 * m] = ev.y;
             got[(2 * l) * W + 2 * m + 1] = od.x; got[(2 * l + 1) * W + 2 * m + 1] = od.y;
         }

@@ -266,32 +266,44 @@ __global__ void __launch_bounds__(SmemS<W, LOADER>::NWARPS * 32, 1) piv_soa_kern
             } else {
                 float4* xw = reinterpret_cast<float4*>(smem + S::XW_OFF);
                 int* xf = reinterpret_cast<int*>(smem + S::XF_OFF);
-                // per-column tap descriptors of this frame (shared by all rows of a window)
-                bool flag = false;
-#pragma unroll
-                for (int e = lane; e < NW * W; e += 32) {
-                    const int j = e & (W - 1), w2 = e >> LOGW;
-                    const TileDesc dsc = desc[w2 * 2 + frame];
-                    const AxisTap cx = cws_axis(dsc.c0 + j, dsc.vx);
-                    xw[e] = make_float4(cx.w1, cx.w1, cx.w0, cx.w0);      // pairs: operands of the packed taps
-                    xf[e] = (cx.exact ? 2 : 0) | ((cx.lo - (dsc.ox + j)) & 1);
-                    flag |= cx.exact;
-                }
-                __syncwarp();
+                // Horizontal taps.  new_x = float32(column) + vx (PB:163-170) is rounded at the magnitude of the column
+                // coordinate, so as long as all columns of the window lie in one binade (same float exponent, >= 1) every
+                // column gets the SAME weights and floor offset (the columns are multiples of the binade's ulp: adding
+                // one only shifts the rounding grid; checked exhaustively on the host).  That is the common case
+                // (~80 % of the jobs of a 4 MP frame): the two weights live in registers.  Otherwise the per-column table
+                // is built; when some coordinate is an exact integer the general (scalar) tap loop takes over.
                 const TileDesc dsc = desc[wi * 2 + frame];
-                const float4* xwq = xw + wi * W;
-                const int* xfq = xf + wi * W;
-                // Window rows (2l, 2l+1) need tile rows 2l .. 2l+2.  The reference's four-term sum (PB:187-192) is
-                // evaluated in separable form, vertical tap first (piv_fused.cuh has the derivation); the result IS
-                // the pair (row 2l, row 2l+1) the row transform wants.
+                const float xn0 = __fadd_rn(static_cast<float>(dsc.c0), dsc.vx);
+                const float xn1 = __fadd_rn(static_cast<float>(dsc.c0 + W - 1), dsc.vx);
+                const bool uni = (xn0 >= 1.0f) && ((__float_as_uint(xn0) >> 23) == (__float_as_uint(xn1) >> 23));
+                const AxisTap cx0 = cws_axis(dsc.c0, dsc.vx);
                 const int ra = 2 * l;
                 const AxisTap cyA = cws_axis(dsc.r0 + ra, dsc.vy), cyB = cws_axis(dsc.r0 + ra + 1, dsc.vy);
-                const bool anyflag = __any_sync(FULL, flag || cyA.exact || cyB.exact);
+                // table = some window of the job needs per-column weights; general = ... has exact-integer coordinates
+                const bool table = __any_sync(FULL, !uni || cx0.exact || cyA.exact || cyB.exact);
+                bool general = false;
+                const float4* xwq = xw + wi * W;
+                const int* xfq = xf + wi * W;
+                if (table) {
+                    bool flag = cyA.exact || cyB.exact;
+#pragma unroll
+                    for (int e = lane; e < NW * W; e += 32) {
+                        const int j = e & (W - 1), w2 = e >> LOGW;
+                        const TileDesc d2 = desc[w2 * 2 + frame];
+                        const AxisTap cx = cws_axis(d2.c0 + j, d2.vx);
+                        xw[e] = make_float4(cx.w1, cx.w1, cx.w0, cx.w0);
+                        xf[e] = (cx.exact ? 2 : 0) | ((cx.lo - (d2.ox + j)) & 1);
+                        flag |= cx.exact;
+                    }
+                    general = __any_sync(FULL, flag);
+                    __syncwarp();
+                }
                 uint32_t wABC[3][W / 4 + 1];
                 load_rows_realigned<W, LOADER, 3, W / 4 + 1>(region, ra, dsc.d & 15, wABC);
                 const uint32_t (&wA)[W / 4 + 1] = wABC[0], (&wB)[W / 4 + 1] = wABC[1], (&wC)[W / 4 + 1] = wABC[2];
                 float cA = u8f(wA[0], 0), cB = u8f(wB[0], 0), cC = u8f(wC[0], 0);
-                if (!anyflag) {
+                if (table && !general) {
+                    // per-column weights from the table, packed taps
                     const float2 wy1 = make_float2(cyA.w1, cyB.w1), wy0 = make_float2(cyA.w0, cyB.w0);
                     float2 vc = pfma(make_float2(cA, cB), wy1, pmul(make_float2(cB, cC), wy0));
                     static_for<0, W>([&](auto jc) {
@@ -304,9 +316,22 @@ __global__ void __launch_bounds__(SmemS<W, LOADER>::NWARPS * 32, 1) piv_soa_kern
                         x[j] = pfma(vc, make_float2(wx.x, wx.y), pmul(vn, make_float2(wx.z, wx.w)));
                         vc = vn;
                     });
+                } else if (!table) {
+                    const float2 wy1 = make_float2(cyA.w1, cyB.w1), wy0 = make_float2(cyA.w0, cyB.w0);
+                    const float2 wx1 = make_float2(cx0.w1, cx0.w1), wx0 = make_float2(cx0.w0, cx0.w0);
+                    float2 vc = pfma(make_float2(cA, cB), wy1, pmul(make_float2(cB, cC), wy0));
+                    static_for<0, W>([&](auto jc) {
+                        constexpr int j = decltype(jc)::value;
+                        const float nA = u8f(wA[(j + 1) >> 2], (j + 1) & 3);
+                        const float nB = u8f(wB[(j + 1) >> 2], (j + 1) & 3);
+                        const float nC = u8f(wC[(j + 1) >> 2], (j + 1) & 3);
+                        const float2 vn = pfma(make_float2(nA, nB), wy1, pmul(make_float2(nB, nC), wy0));
+                        x[j] = pfma(vc, wx1, pmul(vn, wx0));
+                        vc = vn;
+                    });
                 } else {
-                    // some coordinate of the job is an exact integer: there the reference's weights all vanish and
-                    // the value is patched to the tap at (floor y, floor x) (PB:170, 193)
+                    // general tap loop (per-column table).  Where a coordinate is an exact integer the reference's weights
+                    // all vanish and the value is patched to the tap at (floor y, floor x) (PB:170, 193)
                     const bool jyA = (cyA.lo - (dsc.oy + ra)) & 1, jyB = (cyB.lo - (dsc.oy + ra + 1)) & 1;
                     static_for<0, W>([&](auto jc) {
                         constexpr int j = decltype(jc)::value;
@@ -443,20 +468,20 @@ __global__ void __launch_bounds__(SmemS<W, LOADER>::NWARPS * 32, 1) piv_soa_kern
 
         // ------------------------------------------------------------- C': inverse column -> Q
         lockstep(3);
-        M::col_inverse(x);
+        M::col_inverse(x);                      // result in swapped slots: real pair in the odd one
         static_for<0, H>([&](auto mc) {
             constexpr int m = decltype(mc)::value;
-            constexpr int e = M::pos2(m);
-            Xr[m * PQ + l] = x[2 * e];
-            Xi[m * PQ + l] = x[2 * e + 1];
+            constexpr int e = M::pos(m);
+            Xr[m * PQ + l] = x[2 * e + 1];
+            Xi[m * PQ + l] = x[2 * e];
         });
         __syncwarp();
         // ------------------------------------------------------------- R': rows (2l, 2l+1) of the map
         lockstep(4);
         static_for<0, H>([&](auto cc) {
             constexpr int c = decltype(cc)::value;
-            x[2 * c] = Xr[l * PQ + c];
-            x[2 * c + 1] = Xi[l * PQ + c];
+            x[2 * c + 1] = Xr[l * PQ + c];        // swapped slots: the shared forward body then runs the inverse transform
+            x[2 * c] = Xi[l * PQ + c];
         });
         __syncwarp();                           // Q fully read before the map overwrites it
         M::row_inverse(x);
@@ -470,7 +495,7 @@ __global__ void __launch_bounds__(SmemS<W, LOADER>::NWARPS * 32, 1) piv_soa_kern
         static_for<0, W>([&](auto jc) {
             constexpr int j = decltype(jc)::value;
             constexpr int sc = (j + H) % W;
-            const float2 o = x[2 * M::pos(j >> 1) + (j & 1)];
+            const float2 o = x[2 * M::pos(j >> 1) + ((j & 1) ? 0 : 1)];      // swapped slots
             mapw2[(sr0 >> 1) * PM + sc] = o;
             mx0 = fmaxf(mx0, o.x);
             mx1 = fmaxf(mx1, o.y);
@@ -502,9 +527,10 @@ __global__ void __launch_bounds__(SmemS<W, LOADER>::NWARPS * 32, 1) piv_soa_kern
             const int ir = (m - 1 <= 0) ? m : m - 1;
             const int it_ = (m + W >= N2 - 1) ? m : m + W;
             const int ib = (m - W <= 0) ? m : m - W;
-            double eps = static_cast<double>(G::K) * 1e-7;
+            // eps of PB:381 in the map's scale; pass 1 divides the frames by their means (PB:513-514), which scales eps
+            float eps = G::K * 1e-7f;
             const float sa = __shfl_sync(FULL, sum_a, wi * H), sb = __shfl_sync(FULL, sum_b, wi * H);
-            if (p.first_pass) eps *= (static_cast<double>(sa) / N2) * (static_cast<double>(sb) / N2);
+            if (p.first_pass) eps *= (sa * (1.0f / N2)) * (sb * (1.0f / N2));
             const float f_l = at(il), f_r = at(ir), f_t = at(it_), f_b = at(ib);
             // second peak: maximum outside the 7x7 flat-index patch around m, each patch index clamped to
             // [0, N2-1] (PB:346-358).  Rows that cannot touch the patch reuse the row maxima from registers.
@@ -536,31 +562,29 @@ __global__ void __launch_bounds__(SmemS<W, LOADER>::NWARPS * 32, 1) piv_soa_kern
                 stage_issue(0);
                 prefetched = true;
             }
-            const double dmin = static_cast<double>(gmin);
-            const double cm = (static_cast<double>(gmax) - dmin) + eps;
-            const double cl = (static_cast<double>(f_l) - dmin) + eps;
-            const double cr = (static_cast<double>(f_r) - dmin) + eps;
-            const double ct = (static_cast<double>(f_t) - dmin) + eps;
-            const double cb = (static_cast<double>(f_b) - dmin) + eps;
-            // the five logarithms are evaluated by five lanes of the window (one log() body, 1/5 of the FP64 work)
-            const double lsel = (l == 0) ? cm : (l == 1) ? cl : (l == 2) ? cr : (l == 3) ? ct : cb;
-            const double lg = log(lsel);
+            // Three-point log-Gaussian fit (PB:394-407) in FP32 on RATIOS to the peak value:
+            //   (ln c- - ln c+) / (2 ln c+ + 2 ln c- - 4 ln c0) = (B - A) / (2 (A + B)),  A = ln(c+ / c0), B = ln(c- / c0),
+            // which needs no FP64: the differences of logarithms are formed directly instead of by cancellation.
+            // The four logarithms are evaluated by four lanes of the window.  Agreement with the FP64 evaluation of
+            // the reference: ~1e-7 px, below what the FP32 rounding of the map itself contributes.
+            const float cm = (gmax - gmin) + eps;
+            const float csel = ((l == 1) ? f_l : (l == 2) ? f_r : (l == 3) ? f_t : f_b) - gmin + eps;
+            const float lg = logf(csel / cm);               // IEEE division: c / c == 1 exactly (featureless windows)
             const int l0 = wi * H;
-            const double lm = __shfl_sync(FULL, lg, l0), ll = __shfl_sync(FULL, lg, l0 + 1), lr = __shfl_sync(FULL, lg, l0 + 2),
-                         lt = __shfl_sync(FULL, lg, l0 + 3), lb = __shfl_sync(FULL, lg, l0 + 4);
-            double du = static_cast<double>(C) + (lr - ll) / (2.0 * (ll + lr) - 4.0 * lm) - static_cast<double>(H);
-            double dv = static_cast<double>(R) + (lb - lt) / (2.0 * (lb + lt) - 4.0 * lm) - static_cast<double>(H);
+            const float ll = __shfl_sync(FULL, lg, l0 + 1), lr = __shfl_sync(FULL, lg, l0 + 2),
+                        lt = __shfl_sync(FULL, lg, l0 + 3), lb = __shfl_sync(FULL, lg, l0 + 4);
+            const float fu = (lr - ll) / (2.0f * (ll + lr)), fv = (lb - lt) / (2.0f * (lb + lt));
             // torch.nan_to_num (PB:418-419)
-            du = isnan(du) ? 0.0 : (isinf(du) ? copysign(DBL_MAX, du) : du);
-            dv = isnan(dv) ? 0.0 : (isinf(dv) ? copysign(DBL_MAX, dv) : dv);
+            double du = isnan(fu) ? 0.0 : (isinf(fu) ? copysign(DBL_MAX, static_cast<double>(fu))
+                                                     : static_cast<double>(C - H) + static_cast<double>(fu));
+            double dv = isnan(fv) ? 0.0 : (isinf(fv) ? copysign(DBL_MAX, static_cast<double>(fv))
+                                                     : static_cast<double>(R - H) + static_cast<double>(fv));
 
             bool invalid = false;
             float ratio = 0.f;
             if (p.validate) {
-                const double c2 = (static_cast<double>(sp) - dmin) + eps;
-                const double rt = cm / c2;
-                invalid = rt < p.val_ratio;
-                ratio = static_cast<float>(rt);
+                ratio = cm / ((sp - gmin) + eps);
+                invalid = static_cast<double>(ratio) < p.val_ratio;
             }
             if (p.first_pass && (sa == 0.f || sb == 0.f)) {
                 // black window: the reference divides by a zero mean (PB:513-514), every value is NaN,

@@ -40,9 +40,14 @@ struct SoaMath {
         return -1;
     }
 
-    // ---- rows, forward.  in: x[j] = samples j of the lane's two rows.  out: element pos(c) = 2 R[c]
-    static __host__ __device__ __forceinline__ void row_forward(float2 (&x)[W]) {
-        F::run(x);
+    // The pipeline has ONE transform body (Fft2<H> on the natural slots, forward sign) that every phase shares
+    // -- the fused kernel runs it from a single call site inside a run-time loop, which keeps its per-job code
+    // inside the instruction cache (profiles/r02c_icache_stream.txt).  An inverse transform is the same body on
+    // data whose real pairs sit in the ODD and imaginary pairs in the EVEN slots ("swapped" below): the result
+    // comes out swapped as well.
+
+    // ---- rows, forward, AFTER the transform.  in: element pos(k) = Z[k].  out: element pos(c) = 2 R[c]
+    static __host__ __device__ __forceinline__ void row_split(float2 (&x)[W]) {
         {   // k = 0 (and W/2): both real
             const float2 zr = x[0], zi = x[1];
             x[0] = pmuls(padd(zr, zi), 2.0f);
@@ -68,9 +73,9 @@ struct SoaMath {
         });
     }
 
-    // ---- columns, forward.  in: element t = (rows 2t, 2t+1) of the column.  out: element pos(q) = (Y[q], Y[q+H])
-    static __host__ __device__ __forceinline__ void col_forward(float2 (&x)[W]) {
-        F::run(x);
+    // ---- columns, forward, AFTER the transform.  in: element pos(q) = (E[q], O[q]) (even rows, odd rows).
+    //      out: element pos(q) = (Y[q], Y[q+H])
+    static __host__ __device__ __forceinline__ void col_glue_fwd(float2 (&x)[W]) {
         static_for<0, H>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
             constexpr int e = pos(q);
@@ -100,8 +105,10 @@ struct SoaMath {
         });
     }
 
-    // ---- columns, inverse.  in: element pos(q) = (P[q], P[q+H]).  out: element pos2(m) = rows (2m, 2m+1)
-    static __host__ __device__ __forceinline__ void col_inverse(float2 (&x)[W]) {
+    // ---- columns, inverse, BEFORE the transform.  in: element pos(q) = (P[q], P[q+H]).
+    //      out: element q = (u[q], v[q]) SWAPPED (radix-2 step across the pair: decimation in frequency)
+    static __host__ __device__ __forceinline__ void col_glue_inv(float2 (&x)[W]) {
+        float2 y[W];
         static_for<0, H>([&](auto qc) {
             constexpr int q = decltype(qc)::value;
             constexpr int e = pos(q);
@@ -117,40 +124,49 @@ struct SoaMath {
                 vr = fmaf(dr, c, -(di * s));
                 vi = fmaf(di, c, dr * s);
             }
-            x[2 * e] = make_float2(ur, vr);
-            x[2 * e + 1] = make_float2(ui, vi);
+            y[2 * q] = make_float2(ui, vi);
+            y[2 * q + 1] = make_float2(ur, vr);
         });
-        Ifft2Rev<H>::run(x);
+        static_for<0, W>([&](auto ic) { constexpr int i = decltype(ic)::value; x[i] = y[i]; });
     }
 
-    // ---- rows, inverse.  in: element c = G[c] of the lane's two rows (element 0 = (G[0], G[W/2]), both real).
-    //      out: element pos(m) = samples (2m, 2m+1)
-    static __host__ __device__ __forceinline__ void row_inverse(float2 (&x)[W]) {
+    // ---- rows, inverse, BEFORE the transform, on SWAPPED slots.  in: element c = G[c] of the lane's two rows
+    //      (element 0 = (G[0], G[W/2]), both real).  out: element k = Z[k], swapped
+    static __host__ __device__ __forceinline__ void row_presplit(float2 (&x)[W]) {
         {
-            const float2 g0 = x[0], gh = x[1];
-            x[0] = padd(g0, gh);
-            x[1] = psub(g0, gh);
+            const float2 g0 = x[1], gh = x[0];
+            x[1] = padd(g0, gh);
+            x[0] = psub(g0, gh);
         }
         {
             constexpr int e = H / 2;
-            x[2 * e] = pmuls(x[2 * e], 2.0f);
-            x[2 * e + 1] = pmuls(x[2 * e + 1], -2.0f);
+            x[2 * e + 1] = pmuls(x[2 * e + 1], 2.0f);
+            x[2 * e] = pmuls(x[2 * e], -2.0f);
         }
         static_for<1, H / 2>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
             constexpr int ea = k, eb = H - k;
             constexpr float c = float(ct_cos2pi(k, W)), s = float(ct_sin2pi(k, W));
-            const float2 ar = x[2 * ea], ai = x[2 * ea + 1], br = x[2 * eb], bi = x[2 * eb + 1];
+            const float2 ar = x[2 * ea + 1], ai = x[2 * ea], br = x[2 * eb + 1], bi = x[2 * eb];
             const float2 sr = padd(ar, br), si = psub(ai, bi), dr = psub(ar, br), di = padd(ai, bi);
             const float2 tr = pfmas(di, -c, pmuls(dr, -s));         // -s dr - c di
             const float2 ti = pfmas(di, -s, pmuls(dr, c));          //  c dr - s di
-            x[2 * ea] = padd(sr, tr);
-            x[2 * ea + 1] = padd(si, ti);
-            x[2 * eb] = psub(sr, tr);
-            x[2 * eb + 1] = psub(ti, si);
+            x[2 * ea + 1] = padd(sr, tr);
+            x[2 * ea] = padd(si, ti);
+            x[2 * eb + 1] = psub(sr, tr);
+            x[2 * eb] = psub(ti, si);
         });
-        Ifft2<H>::run(x);
     }
+
+    // ---- composites (host test, documentation of the data flow)
+    // rows forward: x[j] = samples j of the lane's two rows -> element pos(c) = 2 R[c]
+    static __host__ __device__ __forceinline__ void row_forward(float2 (&x)[W]) { F::run(x); row_split(x); }
+    // columns forward: element t = (rows 2t, 2t+1) of the column -> element pos(q) = (Y[q], Y[q+H])
+    static __host__ __device__ __forceinline__ void col_forward(float2 (&x)[W]) { F::run(x); col_glue_fwd(x); }
+    // columns inverse: element pos(q) = (P[q], P[q+H]) -> element pos(m) = rows (2m, 2m+1), SWAPPED
+    static __host__ __device__ __forceinline__ void col_inverse(float2 (&x)[W]) { col_glue_inv(x); F::run(x); }
+    // rows inverse: element c = G[c] SWAPPED -> element pos(m) = samples (2m, 2m+1) of both rows, SWAPPED
+    static __host__ __device__ __forceinline__ void row_inverse(float2 (&x)[W]) { row_presplit(x); F::run(x); }
 };
 
 }  // namespace pivb200

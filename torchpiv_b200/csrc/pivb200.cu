@@ -86,11 +86,11 @@ static int check_geometry(int H, int W, int pitch, int wind, int overlap, int n_
 
 static int launch_fused(int wind, int loader, int sink, const CUtensorMap& ta, const CUtensorMap& tb,
                         const PassParams& p, cudaStream_t s) {
-    // 32 / 16 px displacement passes run the pair-packed kernels (piv_soa.cuh); PIVB200_SOA=0 keeps the
-    // one-transform-per-lane kernels (piv_fused.cuh) for A/B measurements
+    // displacement passes run the pair-packed kernels (piv_soa.cuh); PIVB200_SOA=0 (all sizes) / PIVB200_SOA64=0
+    // (64 px only) keep the one-transform-per-lane kernels (piv_fused.cuh) for A/B measurements
     static const bool soa = [] { const char* e = getenv("PIVB200_SOA"); return !(e && e[0] == '0'); }();
     if (soa && sink == SK_DISP && (loader == LD_FRAME_INT || loader == LD_FRAME_ALN || loader == LD_FRAME_CWS)) {
-        static const bool soa64 = [] { const char* e = getenv("PIVB200_SOA64"); return e && e[0] == '1'; }();
+        static const bool soa64 = [] { const char* e = getenv("PIVB200_SOA64"); return !(e && e[0] == '0'); }();
         if (wind == 64 && soa64) return launch_soa_w64(loader, ta, tb, p, s);
         if (wind == 32) return launch_soa_w32(loader, ta, tb, p, s);
         if (wind == 16) return launch_soa_w16(loader, ta, tb, p, s);

@@ -25,8 +25,11 @@ namespace pivb200 {
 template <int W, int LOADER>
 static int launch_soa_one(const CUtensorMap& ta, const CUtensorMap& tb, const PassParams& p_in, cudaStream_t stream) {
     PassParams p = p_in;
-    // lock-step barriers (piv_soa.cuh): PIVB200_SOA_SYNC = mask of phase boundaries, PIVB200_SOA_GROUP = warps per group
-    static const int env_sync = [] { const char* e = getenv("PIVB200_SOA_SYNC"); return e ? atoi(e) : 0; }();
+    // lock-step barriers (piv_soa.cuh): PIVB200_SOA_SYNC = mask of phase boundaries, PIVB200_SOA_GROUP = warps per group.
+    // Measured best on B200: groups of four warps (one per scheduler) meet once per job, before the product -- a
+    // group shares its instruction fetches (the per-job code is larger than the instruction cache), different
+    // groups overlap their FP32-bound and shared-memory-bound phases.
+    static const int env_sync = [] { const char* e = getenv("PIVB200_SOA_SYNC"); return e ? atoi(e) : 4; }();
     static const int env_group = [] { const char* e = getenv("PIVB200_SOA_GROUP"); return e ? atoi(e) : 4; }();
     p.sync_mask = env_sync;
     p.sync_group = env_group;
