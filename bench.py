@@ -446,7 +446,7 @@ def run_ours(args):
     if args.files_pairs > 0:
         cores = os.cpu_count() or 1
         per_rank = max(1, cores // world)
-        decode_threads = max(2, min(8, per_rank // 2))
+        decode_threads = max(2, min(8, per_rank // 4))
         fill_workers = max(1, per_rank - decode_threads)
         barrier()
         t0 = time.perf_counter()

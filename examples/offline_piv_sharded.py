@@ -49,7 +49,8 @@ def main():
                        multipass_mode="CWS", multipass_scale=2.0, dt=12, scale=0.02, folder_mode=args.mode,
                        shard=(rank, world), replace="stencil", statistics=True, batch_pairs=8)
     t0 = time.perf_counter()
-    local_results = [(idx, x, y, u, v) for idx, (x, y, u, v) in zip(piv.pair_indices, piv())]
+    # pairs can be skipped (unreadable frame, ...): take the pair number from the generator, do not count yields
+    local_results = [(piv.last_pair_index, x, y, u, v) for (x, y, u, v) in piv()]
     dt = time.perf_counter() - t0
     results = sharding.gather_results(local_results)                       # pair order, rank 0 only
     state = piv.statistics.state() if piv.statistics is not None else (0, None)

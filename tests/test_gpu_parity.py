@@ -658,3 +658,29 @@ def test_seeded_stress_chained_plans(T):
                 assert (m != om).mean() <= 0.002, (seed, mode, w, o, sc)      # measured worst: 0.066 %
                 assert np.quantile(e, 0.99) < 7e-5, (seed, mode, w, o, sc)      # measured worst: 2.2e-5 px
     print(f"\nstress: worst mask mismatch share {worst_m:.5f}, worst q99 {worst_q:.2e} px")
+
+
+def test_offline_piv_worker_process_hole_filling(T, tmp_path):
+    """fill_workers > 0 moves the reference-exact host post-processing into worker processes: same fields, same
+    order, same skipped pairs, and the generator reports which pair a field belongs to."""
+    from torchpiv_b200 import synth
+    pairs = [cases.small_pair(seed=20 + i, kind="uniform" if i % 2 == 0 else "vortex", zero_patch=(i % 3 == 0))
+             for i in range(7)]
+    synth.write_pair_folder(str(tmp_path), pairs)
+    kw = dict(folder=str(tmp_path), device="cuda:0", file_fmt="bmp", wind_size=64, overlap=32, multipass=2,
+              multipass_mode="CWS", dt=12, scale=0.02, batch_pairs=3)
+    ref_gen = T.OfflinePIV(**kw)
+    ref, ref_idx = [], []
+    for out in ref_gen():
+        ref.append(out)
+        ref_idx.append(ref_gen.last_pair_index)
+    gen = T.OfflinePIV(fill_workers=2, **kw)
+    got, got_idx = [], []
+    for out in gen():
+        got.append(out)
+        got_idx.append(gen.last_pair_index)
+    gen.close()
+    assert got_idx == ref_idx and len(got) == len(ref) > 0
+    for r, g in zip(ref, got):
+        for a, b in zip(r, g):
+            assert np.array_equal(a, b)

@@ -329,6 +329,9 @@ class OfflinePIV:
                         ``"stencil+nmt"``: a normalised median test first widens the invalid set.
     ``fill_workers``    (reference mode) worker PROCESSES for the Delaunay hole filling; 0 (default) fills in the
                         decode threads (Qhull holds the GIL: ~450 pairs/s at 4 MP), N > 0 spreads it over N cores
+    After every ``yield`` the attribute ``last_pair_index`` holds the global index of the pair the field belongs
+    to (pairs may be skipped, so counting the yields is not enough).
+
     ``statistics``      (stencil modes only) accumulate the running sums of the reference worker's
                         statistics (workers.py:79-119) on the device; ``statistics_table()`` returns
                         the table after the run."""
@@ -359,6 +362,7 @@ class OfflinePIV:
         self._decode_threads = max(1, int(decode_threads))
         self._fill_workers = max(0, int(fill_workers))
         self._fill_pool = None
+        self.last_pair_index = None         # global index (into the folder's pair list) of the pair yielded last
         rank, world = shard if shard is not None else (0, 1)
         self.pair_indices = shard_range(len(self._dataset), rank, world)
         self._plan = None
@@ -412,7 +416,10 @@ class OfflinePIV:
             if self._replace != "reference":
                 from .postprocess_device import FieldStatistics, StencilPost
                 g = self._plan.out_geometry
-                post = StencilPost(nmt=self._replace.endswith("nmt"), max_sweeps=max(g.n_rows, g.n_cols))
+                # every sweep is one kernel launch per batch and fills one more ring of a hole: 24 sweeps close
+                # holes up to 48 vectors across (more than a third of a 4 MP field at 16 px spacing -- the
+                # reference gives up on such pairs, PB:305-307); vectors left over are zeroed and stay flagged
+                post = StencilPost(nmt=self._replace.endswith("nmt"), max_sweeps=min(max(g.n_rows, g.n_cols), 24))
                 if self._want_stats:
                     self.statistics = FieldStatistics(g.n_rows, g.n_cols, self._plan.device)
             self._pipe = FramePipeline(self._plan, self._batch_pairs, post=post, stats=self.statistics)
@@ -433,14 +440,40 @@ class OfflinePIV:
                 post-processing (SciPy Delaunay fill in the reference mode) runs on the worker pool too."""
                 u, v, bad = pipe.result(n & 1)
                 batch = batches[n]
-                jobs = [pool.submit(self._finalize, u[i].copy(), v[i].copy(), geo, bad[i])
+                jobs = [(batch.first_pair + i, pool.submit(self._finalize, u[i].copy(), v[i].copy(), geo, bad[i]))
                         for i in range(len(batch)) if ok[batch.index_a[i]] and ok[batch.index_b[i]]]
-                for job in jobs:
+                for pair_index, job in jobs:
                     out = job.result()
-                    if callable(out):             # hole filling still running in a worker process
-                        out = out()
                     if out is not None:
+                        # pairs can be skipped (unreadable frame, hole filling declined): tell which one this is
+                        self.last_pair_index = pair_index
                         yield out
+
+            if self._fill_pool is not None:
+                # reference mode with worker processes: a batch's host post-processing is ONE task of a worker
+                # process; up to 2 x workers batches are in flight, results are yielded in pair order
+                from collections import deque
+                waiting = deque()
+
+                def finish(n, ok):          # noqa: F811 - replaces the in-thread version above
+                    u, v, bad = pipe.result(n & 1)
+                    batch = batches[n]
+                    sel = [i for i in range(len(batch)) if ok[batch.index_a[i]] and ok[batch.index_b[i]]]
+                    if sel:
+                        waiting.append(([batch.first_pair + i for i in sel],
+                                        self._fill_pool.submit_batch(u[sel], v[sel], bad[sel], self._scale, self._dt)))
+                    yield from drain(2 * self._fill_pool.workers)
+
+                def drain(limit):
+                    while len(waiting) > limit:
+                        ids, fut = waiting.popleft()
+                        for pair_index, out in zip(ids, fut.result()):
+                            if out is not None:
+                                self.last_pair_index = pair_index
+                                yield geo.x * self._scale, geo.y * self._scale, out[0], out[1]
+            else:
+                def drain(limit):
+                    return iter(())
 
             decoding = stage(0)
             previous = None                       # (batch number, ok flags) in flight on the GPU
@@ -455,6 +488,7 @@ class OfflinePIV:
                     yield from finish(*previous)
                 previous = (n, ok)
             yield from finish(*previous)
+            yield from drain(0)
 
     def statistics_table(self) -> dict:
         """The reference worker's statistics table (workers.py:100-119) of the pairs processed so far."""
@@ -467,7 +501,7 @@ class OfflinePIV:
         if self._replace != "reference":
             from .postprocess_device import finalize_field_stencil
             return finalize_field_stencil(u, v, geo.x, geo.y, invalid, self._scale, self._dt)
-        return finalize_field(u, v, geo.x, geo.y, invalid, self._scale, self._dt, pool=self._fill_pool)
+        return finalize_field(u, v, geo.x, geo.y, invalid, self._scale, self._dt)
 
     def close(self) -> None:
         """Stop the hole-filling worker processes (``fill_workers`` > 0)."""

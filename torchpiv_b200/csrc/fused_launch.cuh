@@ -54,7 +54,7 @@ static int launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const PassPa
     // PIVB200_NWARPS caps the warps per CTA (occupancy experiments)
     static const int env_warps = [] { const char* e = getenv("PIVB200_NWARPS"); return e ? atoi(e) : 0; }();
     int nwarps = (env_warps > 0 && env_warps < S::NWARPS) ? env_warps : S::NWARPS;
-    if (p.sync_group) nwarps &= ~3;
+    if (p.sync_group) nwarps = (nwarps & ~3) < 4 ? 4 : (nwarps & ~3);       // whole groups of four warps, at least one
     if (p.sync_group >= 4 && nwarps % p.sync_group != 0) p.sync_group = 1;     // groups of N warps need N | nwarps
     long long grid = (njobs + nwarps - 1) / nwarps;
     if (grid > sms) grid = sms;

@@ -123,6 +123,42 @@ struct SmemS {
     static constexpr int CTA_BYTES = NWARPS * STRIDE;
 };
 
+// Request the tiles of `frame` of the warp's current job (TileDesc table in shared memory): TMA for the windows that
+// overlap the frame, byte gather for the rest.  The mbarrier is armed for EVERY (job, frame), also with nothing to
+// wait for, so its phase parity at the matching wait is simply `frame`.  Out of line on purpose: three call sites,
+// and the per-job code has to stay small (instruction cache).
+template <int W, int LOADER>
+__device__ __noinline__ void stage_tiles(const CUtensorMap* tmA, const CUtensorMap* tmB, const PassParams& p,
+                                         unsigned char* smem, int frame, int lane) {
+    using G = GeoS<W>;
+    using T = Tile<W, LOADER>;
+    using S = SmemS<W, LOADER>;
+    constexpr int NW = G::NW;
+    TileDesc* desc = reinterpret_cast<TileDesc*>(smem + S::TD_OFF);
+    const uint32_t bar = smem_u32(smem + S::BAR_OFF);
+    fence_proxy_async();            // generic accesses to the buffers are ordered before the TMA writes
+    __syncwarp();
+    uint32_t tx = 0;
+#pragma unroll 1
+    for (int w2 = 0; w2 < NW; ++w2) {
+        const TileDesc dsc = desc[w2 * 2 + frame];
+        if (dsc.d >= 0) tx += T::TX;
+        else gather_border_tile<W, LOADER>(p, dsc, smem + S::REG_OFF + w2 * G::REGION, frame, lane);
+    }
+    if (lane == 0) {
+        mbar_arrive_expect_tx(bar, tx);
+#pragma unroll 1
+        for (int w2 = 0; w2 < NW; ++w2) {
+            const TileDesc dsc = desc[w2 * 2 + frame];
+            if (dsc.d >= 0)
+                tma_load_3d(smem_u32(smem + S::REG_OFF + w2 * G::REGION), frame ? tmB : tmA, bar, dsc.ox & ~15, dsc.oy, dsc.pair);
+        }
+    }
+    __syncwarp();
+    if (lane < NW && desc[lane * 2 + frame].d < 0) desc[lane * 2 + frame].d = 0;     // gathered tiles start at byte 0
+    __syncwarp();
+}
+
 template <int W, int LOADER>
 __global__ void __launch_bounds__(SmemS<W, LOADER>::NWARPS * 32, 1) piv_soa_kernel(const __grid_constant__ CUtensorMap tmA,
                                                         const __grid_constant__ CUtensorMap tmB,
@@ -184,33 +220,7 @@ __global__ void __launch_bounds__(SmemS<W, LOADER>::NWARPS * 32, 1) piv_soa_kern
         }
         __syncwarp();
     };
-    auto stage_issue = [&](int frame) {
-        TileDesc* desc = reinterpret_cast<TileDesc*>(smem + S::TD_OFF);
-        fence_proxy_async();            // generic accesses to the buffers are ordered before the TMA writes
-        __syncwarp();
-        uint32_t tx = 0;
-#pragma unroll 1
-        for (int w2 = 0; w2 < NW; ++w2) {
-            const TileDesc dsc = desc[w2 * 2 + frame];
-            if (dsc.d >= 0) tx += T::TX;
-            else gather_border_tile<W, LOADER>(p, dsc, smem + S::REG_OFF + w2 * G::REGION, frame, lane);
-        }
-        if (lane == 0) {
-            mbar_arrive_expect_tx(bar, tx);      // armed for every (job, frame): the parity at the wait is `frame`
-#pragma unroll 1
-            for (int w2 = 0; w2 < NW; ++w2) {
-                const TileDesc dsc = desc[w2 * 2 + frame];
-                if (dsc.d >= 0) {
-                    const uint32_t dst = smem_u32(smem + S::REG_OFF + w2 * G::REGION);
-                    if (frame) tma_load_3d(dst, &tmB, bar, dsc.ox & ~15, dsc.oy, dsc.pair);
-                    else tma_load_3d(dst, &tmA, bar, dsc.ox & ~15, dsc.oy, dsc.pair);
-                }
-            }
-        }
-        __syncwarp();
-        if (lane < NW && desc[lane * 2 + frame].d < 0) desc[lane * 2 + frame].d = 0;     // gathered tiles start at byte 0
-        __syncwarp();
-    };
+    auto stage_issue = [&](int frame) { stage_tiles<W, LOADER>(&tmA, &tmB, p, smem, frame, lane); };
 
     // optional lock step (instruction-fetch sharing): bit i of p.sync_mask puts a named barrier over groups of
     // p.sync_group warps at phase boundary i (0 rows, 1 columns, 2 product, 3 inverse columns, 4 inverse rows, 5 epilogue)
@@ -266,43 +276,32 @@ __global__ void __launch_bounds__(SmemS<W, LOADER>::NWARPS * 32, 1) piv_soa_kern
             } else {
                 float4* xw = reinterpret_cast<float4*>(smem + S::XW_OFF);
                 int* xf = reinterpret_cast<int*>(smem + S::XF_OFF);
-                // Horizontal taps.  new_x = float32(column) + vx (PB:163-170) is rounded at the magnitude of the column
-                // coordinate, so as long as all columns of the window lie in one binade (same float exponent, >= 1) every
-                // column gets the SAME weights and floor offset (the columns are multiples of the binade's ulp: adding
-                // one only shifts the rounding grid; checked exhaustively on the host).  That is the common case
-                // (~80 % of the jobs of a 4 MP frame): the two weights live in registers.  Otherwise the per-column table
-                // is built; when some coordinate is an exact integer the general (scalar) tap loop takes over.
+                // per-column tap descriptors of this frame (shared by all rows of a window).  (A variant that keeps the two
+                // weights in registers when all columns of the window lie in one float binade -- then they are identical --
+                // was measured: no gain, and the second copy of the tap loop costs instruction-cache space.)
+                bool flag = false;
+#pragma unroll
+                for (int e = lane; e < NW * W; e += 32) {
+                    const int j = e & (W - 1), w2 = e >> LOGW;
+                    const TileDesc d2 = desc[w2 * 2 + frame];
+                    const AxisTap cx = cws_axis(d2.c0 + j, d2.vx);
+                    xw[e] = make_float4(cx.w1, cx.w1, cx.w0, cx.w0);      // pairs: operands of the packed taps
+                    xf[e] = (cx.exact ? 2 : 0) | ((cx.lo - (d2.ox + j)) & 1);
+                    flag |= cx.exact;
+                }
+                __syncwarp();
                 const TileDesc dsc = desc[wi * 2 + frame];
-                const float xn0 = __fadd_rn(static_cast<float>(dsc.c0), dsc.vx);
-                const float xn1 = __fadd_rn(static_cast<float>(dsc.c0 + W - 1), dsc.vx);
-                const bool uni = (xn0 >= 1.0f) && ((__float_as_uint(xn0) >> 23) == (__float_as_uint(xn1) >> 23));
-                const AxisTap cx0 = cws_axis(dsc.c0, dsc.vx);
-                const int ra = 2 * l;
-                const AxisTap cyA = cws_axis(dsc.r0 + ra, dsc.vy), cyB = cws_axis(dsc.r0 + ra + 1, dsc.vy);
-                // table = some window of the job needs per-column weights; general = ... has exact-integer coordinates
-                const bool table = __any_sync(FULL, !uni || cx0.exact || cyA.exact || cyB.exact);
-                bool general = false;
                 const float4* xwq = xw + wi * W;
                 const int* xfq = xf + wi * W;
-                if (table) {
-                    bool flag = cyA.exact || cyB.exact;
-#pragma unroll
-                    for (int e = lane; e < NW * W; e += 32) {
-                        const int j = e & (W - 1), w2 = e >> LOGW;
-                        const TileDesc d2 = desc[w2 * 2 + frame];
-                        const AxisTap cx = cws_axis(d2.c0 + j, d2.vx);
-                        xw[e] = make_float4(cx.w1, cx.w1, cx.w0, cx.w0);
-                        xf[e] = (cx.exact ? 2 : 0) | ((cx.lo - (d2.ox + j)) & 1);
-                        flag |= cx.exact;
-                    }
-                    general = __any_sync(FULL, flag);
-                    __syncwarp();
-                }
+                const int ra = 2 * l;
+                const AxisTap cyA = cws_axis(dsc.r0 + ra, dsc.vy), cyB = cws_axis(dsc.r0 + ra + 1, dsc.vy);
+                // general = some coordinate of the job is an exact integer (scalar tap loop below)
+                const bool general = __any_sync(FULL, flag || cyA.exact || cyB.exact);
                 uint32_t wABC[3][W / 4 + 1];
                 load_rows_realigned<W, LOADER, 3, W / 4 + 1>(region, ra, dsc.d & 15, wABC);
                 const uint32_t (&wA)[W / 4 + 1] = wABC[0], (&wB)[W / 4 + 1] = wABC[1], (&wC)[W / 4 + 1] = wABC[2];
                 float cA = u8f(wA[0], 0), cB = u8f(wB[0], 0), cC = u8f(wC[0], 0);
-                if (table && !general) {
+                if (!general) {
                     // per-column weights from the table, packed taps
                     const float2 wy1 = make_float2(cyA.w1, cyB.w1), wy0 = make_float2(cyA.w0, cyB.w0);
                     float2 vc = pfma(make_float2(cA, cB), wy1, pmul(make_float2(cB, cC), wy0));
@@ -316,22 +315,9 @@ __global__ void __launch_bounds__(SmemS<W, LOADER>::NWARPS * 32, 1) piv_soa_kern
                         x[j] = pfma(vc, make_float2(wx.x, wx.y), pmul(vn, make_float2(wx.z, wx.w)));
                         vc = vn;
                     });
-                } else if (!table) {
-                    const float2 wy1 = make_float2(cyA.w1, cyB.w1), wy0 = make_float2(cyA.w0, cyB.w0);
-                    const float2 wx1 = make_float2(cx0.w1, cx0.w1), wx0 = make_float2(cx0.w0, cx0.w0);
-                    float2 vc = pfma(make_float2(cA, cB), wy1, pmul(make_float2(cB, cC), wy0));
-                    static_for<0, W>([&](auto jc) {
-                        constexpr int j = decltype(jc)::value;
-                        const float nA = u8f(wA[(j + 1) >> 2], (j + 1) & 3);
-                        const float nB = u8f(wB[(j + 1) >> 2], (j + 1) & 3);
-                        const float nC = u8f(wC[(j + 1) >> 2], (j + 1) & 3);
-                        const float2 vn = pfma(make_float2(nA, nB), wy1, pmul(make_float2(nB, nC), wy0));
-                        x[j] = pfma(vc, wx1, pmul(vn, wx0));
-                        vc = vn;
-                    });
                 } else {
-                    // general tap loop (per-column table).  Where a coordinate is an exact integer the reference's weights
-                    // all vanish and the value is patched to the tap at (floor y, floor x) (PB:170, 193)
+                    // some coordinate of the job is an exact integer: there the reference's weights all vanish and
+                    // the value is patched to the tap at (floor y, floor x) (PB:170, 193)
                     const bool jyA = (cyA.lo - (dsc.oy + ra)) & 1, jyB = (cyB.lo - (dsc.oy + ra + 1)) & 1;
                     static_for<0, W>([&](auto jc) {
                         constexpr int j = decltype(jc)::value;

@@ -134,7 +134,7 @@ static int run_frame_pass(const uint8_t* fa, const uint8_t* fb, int n_pairs, lon
     // aligned in every row: the aligned loader skips the realignment network (PIVB200_NO_ALIGNED=1: A/B knob)
     static const bool no_aligned = [] { const char* e = getenv("PIVB200_NO_ALIGNED"); return e && e[0] == '1'; }();
     if (loader == LD_FRAME_INT && p.sxi == nullptr && p.step % 16 == 0 && !no_aligned) loader = LD_FRAME_ALN;
-    // 64 px first pass: the row transform runs on the tensor cores (PIVB200_TC=0: keep it on the FP32 pipe)
+    // PIVB200_TC=1 (with PIVB200_SOA64=0): experimental 64 px first pass whose row transform runs on the tensor cores
     static const bool use_tc = [] { const char* e = getenv("PIVB200_TC"); return e != nullptr && e[0] == '1'; }();
     if (loader == LD_FRAME_ALN && wind == 64 && sink == SK_DISP && use_tc) loader = LD_FRAME_TC;
     CUtensorMap ta, tb;

@@ -42,42 +42,46 @@ def _neighbour_ring(invalid: np.ndarray) -> np.ndarray:
 
 def _delaunay_fill(support: np.ndarray, values: np.ndarray, targets: np.ndarray):
     """Piecewise-linear (Qhull Delaunay) interpolation of `values` [n, k] given at `support` [n, 2] onto `targets`
-    [m, 2]; None when the triangulation fails.  Module-level so that a worker process can run it."""
+    [m, 2]; None when the triangulation fails."""
     try:
         return LinearNDInterpolator(support, values)(targets)
     except Exception:
         return None
 
 
-class HoleFillPool:
-    """Worker PROCESSES for the Delaunay hole filling of the reference-exact mode.
-
-    Qhull (SciPy) holds the GIL for the 2-6 ms a 4 MP field takes, so threads cannot spread it over the host
-    cores; processes can.  Only the ring points, their values and the hole coordinates travel (tens of KB per
-    pair).  The workers are forked once, when the pool is built (before the decode threads start), and only ever run
-    NumPy / SciPy code -- the same arrangement as torch's DataLoader workers next to a CUDA parent; "spawn" would
-    re-import the user's main script in every worker."""
-
-    def __init__(self, workers: int):
-        import multiprocessing as mp
-        from concurrent.futures import ProcessPoolExecutor
-        self.workers = int(workers)
-        self._pool = ProcessPoolExecutor(max_workers=self.workers, mp_context=mp.get_context("fork"))
-        # start every worker now (the first submit would otherwise pay the interpreter start-up one by one)
-        list(self._pool.map(_warm, range(self.workers)))
-
-    def submit(self, support, values, targets):
-        return self._pool.submit(_delaunay_fill, support, values, targets)
-
-    def shutdown(self):
-        self._pool.shutdown(wait=False, cancel_futures=True)
+def _finalize_batch(u, v, invalid, scale, dt):
+    """Worker-process task: finalize_uv for every pair of a batch.  Returns a list of (u, v) or None per pair."""
+    return [finalize_uv(u[i], v[i], invalid[i], scale, dt) for i in range(u.shape[0])]
 
 
 def _warm(i):
     return i
 
 
-def fill_holes(field: np.ndarray, *more: np.ndarray, pool: "HoleFillPool | None" = None):
+class HoleFillPool:
+    """Worker PROCESSES for the host post-processing of the reference-exact mode (one task per batch of pairs).
+
+    Qhull (SciPy) holds the GIL for the 2-6 ms a 4 MP field takes, and the NumPy glue around it is GIL-bound too,
+    so threads cannot spread it over the host cores; processes can.  The workers are forked once, when the pool is
+    built (before the decode threads start), and only ever run NumPy / SciPy code -- the same arrangement as torch's
+    DataLoader workers next to a CUDA parent; "spawn" would re-import the user's main script in every worker."""
+
+    def __init__(self, workers: int):
+        import multiprocessing as mp
+        from concurrent.futures import ProcessPoolExecutor
+        self.workers = int(workers)
+        self._pool = ProcessPoolExecutor(max_workers=self.workers, mp_context=mp.get_context("fork"))
+        # start every worker now (the first submit would otherwise pay the fork one by one)
+        list(self._pool.map(_warm, range(self.workers)))
+
+    def submit_batch(self, u, v, invalid, scale, dt):
+        return self._pool.submit(_finalize_batch, u, v, invalid, scale, dt)
+
+    def shutdown(self):
+        self._pool.shutdown(wait=False, cancel_futures=True)
+
+
+def fill_holes(field: np.ndarray, *more: np.ndarray):
     """Fill NaNs by piecewise-linear (Delaunay) interpolation over the ring of valid neighbours.
     Returns None -- the caller then skips the pair, as the reference does -- when the ring is
     empty (no invalid vector at all), when the triangulation fails, or when the ring covers a
@@ -100,9 +104,6 @@ def fill_holes(field: np.ndarray, *more: np.ndarray, pool: "HoleFillPool | None"
         return None
     values = np.stack([f[ring] for f in fields], axis=1)
     targets = np.argwhere(invalid)
-    if pool is not None:
-        # asynchronous: the caller resolves the future with finish_fill()
-        return _PendingFill(fields, invalid, pool.submit(support, values, targets), bool(more))
     filled = _delaunay_fill(support, values, targets)
     if filled is None:
         return None
@@ -111,41 +112,19 @@ def fill_holes(field: np.ndarray, *more: np.ndarray, pool: "HoleFillPool | None"
     return fields if more else field
 
 
-class _PendingFill:
-    """A hole filling running in a worker process."""
-
-    def __init__(self, fields, invalid, future, many):
-        self.fields, self.invalid, self.future, self.many = fields, invalid, future, many
-
-    def result(self):
-        filled = self.future.result()
-        if filled is None:
-            return None
-        for k, f in enumerate(self.fields):
-            f[self.invalid] = filled[:, k]
-        return self.fields if self.many else self.fields[0]
-
-
-def finalize_field(u, v, x, y, invalid, scale: float = 1.0, dt: float = 1.0, pool=None):
-    """u, v in px (float64, modified in place) -> (x, y, u, v) in mm and m/s, or None to skip.
-    With ``pool`` (HoleFillPool) the Delaunay fill runs in a worker process and a zero-argument callable that
-    completes the field is returned instead."""
+def finalize_uv(u, v, invalid, scale: float = 1.0, dt: float = 1.0):
+    """u, v in px (float64, modified in place) -> (u, v) in m/s, rows flipped, v negated; None to skip the pair."""
     if invalid is not None:
         u[invalid] = np.nan
         v[invalid] = np.nan
-        filled = fill_holes(fill_borders(u), fill_borders(v), pool=pool)
+        filled = fill_holes(fill_borders(u), fill_borders(v))
         if filled is None:
             return None
-        if isinstance(filled, _PendingFill):
-            def complete(pending=filled):
-                done = pending.result()
-                return None if done is None else _to_units(done[0], done[1], x, y, scale, dt)
-            return complete
         u, v = filled
-    return _to_units(u, v, x, y, scale, dt)
+    return np.flip(u, axis=0) * scale / dt * 1000, -np.flip(v, axis=0) * scale / dt * 1000
 
 
-def _to_units(u, v, x, y, scale, dt):
-    u = np.flip(u, axis=0) * scale / dt * 1000
-    v = -np.flip(v, axis=0) * scale / dt * 1000
-    return x * scale, y * scale, u, v
+def finalize_field(u, v, x, y, invalid, scale: float = 1.0, dt: float = 1.0):
+    """u, v in px (float64, modified in place) -> (x, y, u, v) in mm and m/s, or None to skip."""
+    out = finalize_uv(u, v, invalid, scale, dt)
+    return None if out is None else (x * scale, y * scale, out[0], out[1])
