@@ -222,6 +222,7 @@ def cpu_oracle_rate(n_pairs: int, warmup: int = 0):
 def cpu_reference_rate(n_pairs: int, warmup: int):
     """(pairs/s, seconds, kind, what) of the reference path on the host cores."""
     import torch
+    torch.set_num_threads(os.cpu_count() or 1)        # torchrun exports OMP_NUM_THREADS=1
     PB = load_reference()
     if PB is not None:
         rate, dt = reference_pass_rate(PB, torch.device("cpu"), make_pairs(min(n_pairs, 2), seed0=100), n_pairs, warmup)
@@ -539,7 +540,10 @@ def run_ours(args):
     # ---- CPU baseline (bounded sample): the reference on the host cores --------------------------
     cores = os.cpu_count() or 1
     n_cpu = args.cpu_pairs
-    cpu_rate, cpu_dt, cpu_kind, cpu_what = cpu_reference_rate(n_cpu, warmup=1)
+    if n_cpu > 0:
+        cpu_rate, cpu_dt, cpu_kind, cpu_what = cpu_reference_rate(n_cpu, warmup=1)
+    else:
+        cpu_rate, cpu_dt, cpu_kind, cpu_what = None, 0.0, None, "skipped (--cpu-pairs 0)"
     # ---- the reference's own torch-CUDA path on this GPU (bounded sample) -------------------------
     torch_cuda = None
     if args.torch_pairs > 0:
