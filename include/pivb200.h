@@ -117,7 +117,12 @@ int pivb200_corr_to_disp(void* corr, int dtype, long long n, int d, int k, int v
 
 /* The shifted interrogation windows as the fused pass sees them (TMA tile + in-tile taps),
  * float32 [N, wind, wind] each.  mode/shift as in pivb200_pass_next; shift_x = NULL with
- * MODE_DWS gives the unshifted windows = moving_window_array (PB:220-247). */
+ * MODE_DWS gives the unshifted windows = moving_window_array (PB:220-247).
+ * Unshifted and MODE_DWS windows are BIT-EXACT with the reference.  MODE_CWS windows are NOT: the fused
+ * loader evaluates the reference's four-term bilinear sum (PB:187-192) in separable form (vertical tap,
+ * then horizontal tap), which differs from it by FP32 rounding -- at most 2^-14 grey levels (observed
+ * <= 4e-5 of 0..255), far inside the 1e-3 px tolerance of the displacements.  pivb200_bilinear_cws below
+ * keeps the reference's exact evaluation order and IS bit-exact. */
 int pivb200_windows(const uint8_t* frames_a, const uint8_t* frames_b, int n_pairs,
                     long long pair_stride, int H, int W, int pitch, int wind, int overlap,
                     int mode, const void* shift_x, const void* shift_y, float* win_a,

@@ -684,3 +684,24 @@ def test_offline_piv_worker_process_hole_filling(T, tmp_path):
     for r, g in zip(ref, got):
         for a, b in zip(r, g):
             assert np.array_equal(a, b)
+
+
+def test_device_guard_on_a_non_current_device(T):
+    """The C ABI launches on the CURRENT device: the Python layer has to make the tensors' device current for the
+    call (round-1 advisor finding).  Needs two GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    a, b = cases.small_pair(seed=2)
+    assert torch.cuda.current_device() == 0
+    dev = torch.device("cuda", 1)
+    fa, fb = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+    u1, v1, x1, y1, m1 = T.extended_search_area_piv(fa, fb, window_size=32, overlap=16, validate=True)
+    u0, v0, x0, y0, m0 = T.extended_search_area_piv(fa.to("cuda:0"), fb.to("cuda:0"), window_size=32, overlap=16,
+                                                    validate=True)
+    assert np.array_equal(u1, u0) and np.array_equal(v1, v0) and np.array_equal(m1, m0)
+    plan = T.PIVPlan(a.shape, 64, 32, 2, "CWS", 2.0, device=dev)
+    pu, pv, pm = plan.run(fa, fb)
+    ref = T.PIVPlan(a.shape, 64, 32, 2, "CWS", 2.0, device="cuda:0")
+    ru, rv, rm = ref.run(fa.to("cuda:0"), fb.to("cuda:0"))
+    assert torch.equal(pu.cpu(), ru.cpu()) and torch.equal(pm.cpu(), rm.cpu())
+    assert torch.cuda.current_device() == 0

@@ -29,6 +29,20 @@
 
 namespace pivb200 {
 
+// byte b of `word` as a float without the quarter-rate XU pipe: PRMT (ALU) isolates the byte, I2FP.F32.S32 (a
+// full-rate FMA-pipe conversion; inline PTX keeps ptxas from fusing the pair back into the XU's I2F.U8) converts it.
+// PIVB200_XU_CVT=1 (compile time) restores I2F.U8 for A/B runs.
+__device__ __forceinline__ float u8g(uint32_t word, int b) {
+#ifdef PIVB200_XU_CVT
+    return u8f(word, b);
+#else
+    const uint32_t x = __byte_perm(word, 0u, 0x4440u + static_cast<uint32_t>(b));
+    float f;
+    asm("cvt.rn.f32.s32 %0, %1;" : "=f"(f) : "r"(x));
+    return f;
+#endif
+}
+
 template <int W>
 struct GeoS {
     static_assert(W == 16 || W == 32 || W == 64, "window size");
@@ -271,7 +285,7 @@ __global__ void __launch_bounds__(SmemS<W, LOADER>::NWARPS * 32, 1) piv_soa_kern
                 }
                 static_for<0, W>([&](auto jc) {
                     constexpr int j = decltype(jc)::value;
-                    x[j] = make_float2(u8f(w[0][j >> 2], j & 3), u8f(w[1][j >> 2], j & 3));
+                    x[j] = make_float2(u8g(w[0][j >> 2], j & 3), u8g(w[1][j >> 2], j & 3));
                 });
             } else {
                 float4* xw = reinterpret_cast<float4*>(smem + S::XW_OFF);
@@ -300,16 +314,16 @@ __global__ void __launch_bounds__(SmemS<W, LOADER>::NWARPS * 32, 1) piv_soa_kern
                 uint32_t wABC[3][W / 4 + 1];
                 load_rows_realigned<W, LOADER, 3, W / 4 + 1>(region, ra, dsc.d & 15, wABC);
                 const uint32_t (&wA)[W / 4 + 1] = wABC[0], (&wB)[W / 4 + 1] = wABC[1], (&wC)[W / 4 + 1] = wABC[2];
-                float cA = u8f(wA[0], 0), cB = u8f(wB[0], 0), cC = u8f(wC[0], 0);
+                float cA = u8g(wA[0], 0), cB = u8g(wB[0], 0), cC = u8g(wC[0], 0);
                 if (!general) {
                     // per-column weights from the table, packed taps
                     const float2 wy1 = make_float2(cyA.w1, cyB.w1), wy0 = make_float2(cyA.w0, cyB.w0);
                     float2 vc = pfma(make_float2(cA, cB), wy1, pmul(make_float2(cB, cC), wy0));
                     static_for<0, W>([&](auto jc) {
                         constexpr int j = decltype(jc)::value;
-                        const float nA = u8f(wA[(j + 1) >> 2], (j + 1) & 3);
-                        const float nB = u8f(wB[(j + 1) >> 2], (j + 1) & 3);
-                        const float nC = u8f(wC[(j + 1) >> 2], (j + 1) & 3);
+                        const float nA = u8g(wA[(j + 1) >> 2], (j + 1) & 3);
+                        const float nB = u8g(wB[(j + 1) >> 2], (j + 1) & 3);
+                        const float nC = u8g(wC[(j + 1) >> 2], (j + 1) & 3);
                         const float2 vn = pfma(make_float2(nA, nB), wy1, pmul(make_float2(nB, nC), wy0));
                         const float4 wx = xwq[j];
                         x[j] = pfma(vc, make_float2(wx.x, wx.y), pmul(vn, make_float2(wx.z, wx.w)));
@@ -321,9 +335,9 @@ __global__ void __launch_bounds__(SmemS<W, LOADER>::NWARPS * 32, 1) piv_soa_kern
                     const bool jyA = (cyA.lo - (dsc.oy + ra)) & 1, jyB = (cyB.lo - (dsc.oy + ra + 1)) & 1;
                     static_for<0, W>([&](auto jc) {
                         constexpr int j = decltype(jc)::value;
-                        const float nA = u8f(wA[(j + 1) >> 2], (j + 1) & 3);
-                        const float nB = u8f(wB[(j + 1) >> 2], (j + 1) & 3);
-                        const float nC = u8f(wC[(j + 1) >> 2], (j + 1) & 3);
+                        const float nA = u8g(wA[(j + 1) >> 2], (j + 1) & 3);
+                        const float nB = u8g(wB[(j + 1) >> 2], (j + 1) & 3);
+                        const float nC = u8g(wC[(j + 1) >> 2], (j + 1) & 3);
                         const float4 wx4 = xwq[j];
                         const float2 wx = make_float2(wx4.x, wx4.z);
                         const int fl = xfq[j];
