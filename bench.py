@@ -258,7 +258,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def files_leg(T, synth, dev, rank, world, n_pairs_total, decode_threads, fill_workers):
+def files_leg(T, synth, dev, rank, world, n_pairs_total, decode_threads, fill_workers, per_rank):
     """BASELINE config 5: a sequential-mode folder of 4 MP bmp files through the public generator
     OfflinePIV(...)() (decode threads -> pinned staging -> H2D -> fused passes -> D2H -> host post-processing),
     sharded by pair index over the ranks (shard=(rank, world), no collective).  K unique frames are written once
@@ -282,12 +282,12 @@ def files_leg(T, synth, dev, rank, world, n_pairs_total, decode_threads, fill_wo
         os.makedirs(folder)
         for i in range(n_pairs_total + 1):
             os.link(uniq[i % K], os.path.join(folder, f"frame{i:05d}.bmp"))
-        for mode, kw in (("reference", dict(replace="reference", fill_workers=fill_workers)),
-                         ("stencil", dict(replace="stencil"))):
+        # reference mode: a few decode threads + worker processes for Qhull; stencil mode: every core decodes
+        for mode, kw in (("reference", dict(replace="reference", fill_workers=fill_workers, decode_threads=decode_threads)),
+                         ("stencil", dict(replace="stencil", decode_threads=max(2, per_rank - 4)))):
             piv = T.OfflinePIV(folder=folder, device=f"cuda:{dev.index}", file_fmt="bmp", wind_size=WIND, overlap=OVERLAP,
                                multipass=PASSES, multipass_mode=MODE, multipass_scale=SCALE, dt=12, scale=0.02,
-                               folder_mode="sequential", batch_pairs=32, decode_threads=decode_threads,
-                               shard=(rank, world), **kw)
+                               folder_mode="sequential", batch_pairs=32, shard=(rank, world), **kw)
             n = 0
             t0 = time.perf_counter()
             for _ in piv():
@@ -448,10 +448,12 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         per_rank = max(1, cores // world)
         decode_threads = max(2, min(8, per_rank // 4))
-        fill_workers = max(1, per_rank - decode_threads)
+        # measured on the 16-vCPU box (tools/_files_sweep.py): 4 decode threads + 6 worker processes; more workers
+        # oversubscribe the cores (main thread, CUDA and executor threads need theirs) and the rate drops again
+        fill_workers = max(2, (3 * per_rank) // 8)
         barrier()
         t0 = time.perf_counter()
-        res = files_leg(T, synth, dev, rank, world, args.files_pairs, decode_threads, fill_workers)
+        res = files_leg(T, synth, dev, rank, world, args.files_pairs, decode_threads, fill_workers, per_rank)
         files = {}
         for mode, (n_yield, n_pairs, secs) in res.items():
             t_max = max_over_ranks(secs * 1e3) * 1e-3

@@ -265,3 +265,27 @@ def test_read_gray_into_fast_bmp_path_equals_opencv(tmp_path):
     assert not dataset.read_gray_into(trunc, np.empty((128, 256), dtype=np.uint8))
     assert not dataset.read_gray_into(str(tmp_path / "missing.bmp"), dst)
     assert not dataset.read_gray_into(files["synth"], np.empty((5, 5), dtype=np.uint8))
+
+
+def test_hole_fill_pool_matches_inline_fill():
+    """The worker-process post-processing (shared-memory slots, forked workers) returns exactly what the in-thread
+    path returns, including pairs the reference would skip (no invalid vector at all -> None)."""
+    from torchpiv_b200 import postprocess as P
+    rng = np.random.default_rng(3)
+    n, m, B = 37, 41, 5
+    u, v = rng.normal(size=(B, n, m)), rng.normal(size=(B, n, m))
+    inv = rng.random((B, n, m)) < 0.01
+    inv[:, 10:15, 20:27] = True
+    inv[3] = False                                  # the reference skips such a pair (PB:299-304)
+    ref = [P.finalize_uv(u[i].copy(), v[i].copy(), inv[i], 0.5, 2.0) for i in range(B)]
+    pool = P.HoleFillPool(2, B, n, m)
+    try:
+        handles = [pool.submit_batch(u, v, inv, 0.5, 2.0) for _ in range(pool.capacity)]
+        for h in handles:
+            got = pool.collect(h)
+            assert [g is None for g in got] == [r is None for r in ref] and ref[3] is None
+            for g, r in zip(got, ref):
+                if r is not None:
+                    assert np.array_equal(g[0], r[0]) and np.array_equal(g[1], r[1])
+    finally:
+        pool.shutdown()

@@ -427,7 +427,7 @@ class OfflinePIV:
         geo = self._plan.out_geometry
         if self._fill_workers and self._replace == "reference" and self._fill_pool is None:
             from .postprocess import HoleFillPool
-            self._fill_pool = HoleFillPool(self._fill_workers)
+            self._fill_pool = HoleFillPool(self._fill_workers, self._batch_pairs, geo.n_rows, geo.n_cols)
 
         with ThreadPoolExecutor(max_workers=self._decode_threads) as pool:
             def stage(n):
@@ -462,12 +462,12 @@ class OfflinePIV:
                     if sel:
                         waiting.append(([batch.first_pair + i for i in sel],
                                         self._fill_pool.submit_batch(u[sel], v[sel], bad[sel], self._scale, self._dt)))
-                    yield from drain(2 * self._fill_pool.workers)
+                    yield from drain(self._fill_pool.capacity - 1)
 
                 def drain(limit):
                     while len(waiting) > limit:
-                        ids, fut = waiting.popleft()
-                        for pair_index, out in zip(ids, fut.result()):
+                        ids, handle = waiting.popleft()
+                        for pair_index, out in zip(ids, self._fill_pool.collect(handle)):
                             if out is not None:
                                 self.last_pair_index = pair_index
                                 yield geo.x * self._scale, geo.y * self._scale, out[0], out[1]

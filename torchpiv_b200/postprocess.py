@@ -49,9 +49,23 @@ def _delaunay_fill(support: np.ndarray, values: np.ndarray, targets: np.ndarray)
         return None
 
 
-def _finalize_batch(u, v, invalid, scale, dt):
-    """Worker-process task: finalize_uv for every pair of a batch.  Returns a list of (u, v) or None per pair."""
-    return [finalize_uv(u[i], v[i], invalid[i], scale, dt) for i in range(u.shape[0])]
+# Shared slots between the parent and its forked workers: {"U": [slots, B, n, m] f64, "V": ..., "M": uint8, "OK": [slots, B]}
+_SLOTS = None
+
+
+def _finalize_slot(slot, count, scale, dt):
+    """Worker-process task: finalize_uv for the `count` pairs of a shared slot, IN PLACE (the finished u, v replace the
+    raw ones; OK[slot, i] = 0 marks a pair the reference would skip)."""
+    U, V, M, OK = _SLOTS["U"], _SLOTS["V"], _SLOTS["M"], _SLOTS["OK"]
+    for i in range(count):
+        out = finalize_uv(U[slot, i], V[slot, i], M[slot, i].view(np.bool_), scale, dt)
+        if out is None:
+            OK[slot, i] = 0
+        else:
+            OK[slot, i] = 1
+            U[slot, i] = out[0]
+            V[slot, i] = out[1]
+    return count
 
 
 def _warm(i):
@@ -62,20 +76,56 @@ class HoleFillPool:
     """Worker PROCESSES for the host post-processing of the reference-exact mode (one task per batch of pairs).
 
     Qhull (SciPy) holds the GIL for the 2-6 ms a 4 MP field takes, and the NumPy glue around it is GIL-bound too,
-    so threads cannot spread it over the host cores; processes can.  The workers are forked once, when the pool is
-    built (before the decode threads start), and only ever run NumPy / SciPy code -- the same arrangement as torch's
-    DataLoader workers next to a CUDA parent; "spawn" would re-import the user's main script in every worker."""
+    so threads cannot spread it over the host cores; processes can.  The fields travel through anonymous shared
+    memory mapped BEFORE the workers are forked (a batch is 8.5 MB; pickling it through the executor's pipes costs
+    more than the triangulations), only slot numbers go through the task queue.  The workers are forked once, when
+    the pool is built (before the decode threads start), and only ever run NumPy / SciPy code -- the same
+    arrangement as torch's DataLoader workers next to a CUDA parent; "spawn" would re-import the user's main script
+    in every worker."""
 
-    def __init__(self, workers: int):
+    def __init__(self, workers: int, batch_pairs: int, n_rows: int, n_cols: int):
+        import mmap
         import multiprocessing as mp
         from concurrent.futures import ProcessPoolExecutor
+        global _SLOTS
         self.workers = int(workers)
+        self.n_slots = 2 * self.workers + 2
+        B, n, m = int(batch_pairs), int(n_rows), int(n_cols)
+        f_bytes, m_bytes = self.n_slots * B * n * m * 8, self.n_slots * B * n * m
+        self._maps = [mmap.mmap(-1, f_bytes), mmap.mmap(-1, f_bytes), mmap.mmap(-1, m_bytes), mmap.mmap(-1, self.n_slots * B)]
+        shape = (self.n_slots, B, n, m)
+        self._views = {"U": np.frombuffer(self._maps[0], np.float64).reshape(shape),
+                       "V": np.frombuffer(self._maps[1], np.float64).reshape(shape),
+                       "M": np.frombuffer(self._maps[2], np.uint8).reshape(shape),
+                       "OK": np.frombuffer(self._maps[3], np.uint8).reshape(self.n_slots, B)}
+        _SLOTS = self._views                      # inherited by the forked workers
+        self._free = list(range(self.n_slots))
         self._pool = ProcessPoolExecutor(max_workers=self.workers, mp_context=mp.get_context("fork"))
         # start every worker now (the first submit would otherwise pay the fork one by one)
         list(self._pool.map(_warm, range(self.workers)))
 
+    @property
+    def capacity(self) -> int:
+        """Batches that can be in flight."""
+        return self.n_slots
+
     def submit_batch(self, u, v, invalid, scale, dt):
-        return self._pool.submit(_finalize_batch, u, v, invalid, scale, dt)
+        """u, v [k, n, m] float64, invalid [k, n, m] bool -> a handle for :meth:`collect`."""
+        slot = self._free.pop()
+        k = u.shape[0]
+        self._views["U"][slot, :k] = u
+        self._views["V"][slot, :k] = v
+        self._views["M"][slot, :k] = invalid
+        return self._pool.submit(_finalize_slot, slot, k, scale, dt), slot, k
+
+    def collect(self, handle):
+        """Wait for a batch; returns a list of (u, v) copies or None per pair and frees the slot."""
+        fut, slot, k = handle
+        fut.result()
+        U, V, OK = self._views["U"], self._views["V"], self._views["OK"]
+        out = [(U[slot, i].copy(), V[slot, i].copy()) if OK[slot, i] else None for i in range(k)]
+        self._free.append(slot)
+        return out
 
     def shutdown(self):
         self._pool.shutdown(wait=False, cancel_futures=True)
