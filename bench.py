@@ -620,8 +620,8 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=3, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--torch-pairs", type=int, default=24,
                     help="size of the bounded reference-on-GPU sample (0 = skip)")
-    ap.add_argument("--files-pairs", type=int, default=2048,
-                    help="pairs of the from-files leg (BASELINE config 5; 4000 = the full configuration, 0 = skip)")
+    ap.add_argument("--files-pairs", type=int, default=4000,
+                    help="pairs of the from-files leg (BASELINE config 5: 4 000 pairs = 4 001 files; 0 = skip)")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # convenience: re-launch under torchrun, one rank per GPU

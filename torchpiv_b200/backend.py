@@ -449,6 +449,21 @@ class OfflinePIV:
                         self.last_pair_index = pair_index
                         yield out
 
+            if self._replace != "reference":
+                # stencil modes: the holes were filled on the device; what is left (flip, sign, units: PB:894-900) is
+                # done for the whole batch at once -- per-pair NumPy calls in the (GIL-sharing) decode threads were
+                # the bottleneck of the from-files path
+                def finish(n, ok):          # noqa: F811 - replaces the in-thread version above
+                    u, v, bad = pipe.result(n & 1)
+                    batch = batches[n]
+                    # same elementwise operation order as the reference (PB:896-897)
+                    U = np.flip(u[:len(batch)], axis=1) * self._scale / self._dt * 1000
+                    V = -np.flip(v[:len(batch)], axis=1) * self._scale / self._dt * 1000
+                    for i in range(len(batch)):
+                        if ok[batch.index_a[i]] and ok[batch.index_b[i]]:
+                            self.last_pair_index = batch.first_pair + i
+                            yield geo.x * self._scale, geo.y * self._scale, U[i], V[i]
+
             if self._fill_pool is not None:
                 # reference mode with worker processes: a batch's host post-processing is ONE task of a worker
                 # process; up to 2 x workers batches are in flight, results are yielded in pair order
