@@ -246,7 +246,11 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64 (pass 1) / f32 (pass 2), as the reference computes", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": pairs_per_step, "device": "cpu", "note": what},
+        # same keys as the GPU arm's config (the sample is bounded: one pair per step on the host cores)
+        "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": pairs_per_step, "batches_per_step": 1,
+                   "pairs_per_batch": pairs_per_step, "frame_bytes_per_batch_per_gpu": 2 * pairs_per_step * SHAPE[0] * SHAPE[1],
+                   "l2_policy": "n/a (host cores)", "sharding": "rank 0 only"},
+        "reference": {"device": "cpu", "what": what},
         "cpu_baseline": {"value": rate, "unit": "pairs/s", "cores": cores, "kind": kind,
                          "sample": f"{args.steps} x 1 4MP pair, 2-pass CWS, pass functions only (no image decode)"},
         "e2e": {"value": rate, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
