@@ -1,4 +1,5 @@
-// Fused PIV pass kernel, pair-packed variant (32 px and 16 px windows, displacement sink) for sm_100a.
+// Fused PIV pass kernel, pair-packed variant (64 / 32 / 16 px windows, displacement sink) for sm_100a: the
+// kernel behind pivb200_pass_first / pivb200_pass_next (OfflinePIV, PIVPlan).
 //
 // Same job as piv_fused_kernel (window extraction by TMA -> CWS / DWS window shift -> 2-D cross-correlation
 // -> fft-shifted peak search, sub-pixel fit, peak-ratio validation, predictor glue; PB:147-257, 346-422,
@@ -7,22 +8,22 @@
 // piv_soa_math.cuh) instead of one W-point transform on (re, im)-packed registers:
 //
 //   R   lane l transforms window rows (2l, 2l+1) as the pair: real rows -> H-point complex FFT + split
-//       step -> quads (re pair, im pair) X [row pair l][column c] in shared memory (STS.128)
-//   C   lane c reads column c (LDS.128): the pair is (even rows, odd rows); H-point FFT + radix-2 step
-//       across the pair -> (Y[q], Y[q+H]).  Frame a's spectrum is PARKED in tensor memory (lane-private
-//       scratch: tcgen05.st / ld) while frame b goes through R and C
+//       step -> planes X [row pair l][column c] of real pairs and of imaginary pairs in shared memory (STS.64)
+//   C   lane c reads column c: the pair is (even rows, odd rows); H-point FFT + radix-2 step across the
+//       pair -> (Y[q], Y[q+H]).  Frame a's spectrum is PARKED in tensor memory (lane-private scratch:
+//       tcgen05.st / ld) while frame b goes through R and C
 //   P   conj(A^) B^ (packed); column 0 (= the two real columns 0 and W/2) is separated with the help of
-//       the other lanes through a scratch area, as in piv_fused_kernel
-//   C'  radix-2 step across the pair, inverse H-point FFT -> quads Q [row pair m][column c]
+//       the other lanes through a scratch area
+//   C'  radix-2 step across the pair, inverse H-point FFT -> planes Q [row pair m][column c]
 //   R'  lane l reads the half spectra of rows (2l, 2l+1), inverse real transform -> two rows of the map
-//   E   epilogue: min / first-max / flat neighbours / second peak / FP64 fit on the fft-shifted map
+//   E   epilogue: min / first-max / flat neighbours / second peak / FP32 ratio fit on the fft-shifted map
 //
-// Versus piv_fused_kernel<32, ...>: all FFT arithmetic is packed FADD2 / FMUL2 / FFMA2 with immediate
-// twiddles (the radix-2 steps across a pair are the only scalar FP32 work), every exchange is a 128-bit
-// shared-memory access (a third of the LDS / STS instructions), the per-lane state is 64 data registers
-// for a 16-point pair transform instead of a 32-point transform plus its temporaries, so 20 warps are
-// resident instead of 16 with no spills, and the code (~25 KB) fits the instruction cache without the
-// shared run-time FFT body.
+// Versus piv_fused_kernel: all FFT arithmetic is packed FADD2 / FMUL2 / FFMA2 with immediate twiddles (the
+// radix-2 steps across a pair are the only scalar FP32 work), 13-22 % fewer executed instructions, 76-104 bytes
+// of spills instead of 472 at 64 px, 20 instead of 16 resident warps at 32 px.  What bounds both generations is
+// instruction supply: the per-job code (46 KB at 32 px CWS, 72 KB at 64 px) is larger than what an SM streams at
+// full rate (~44 KB, tests/micro/icache_stream.cu); DESIGN.md section 3.1 has the measurements and the list of
+// restructurings that were tried.
 #pragma once
 #include "piv_fused.cuh"
 #include "piv_soa_math.cuh"
