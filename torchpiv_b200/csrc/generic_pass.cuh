@@ -3,20 +3,41 @@
 //
 // The fused in-register FFT kernels (piv_fused.cuh) exist for 16 / 32 / 64 px only.  Everything else
 // takes this path: one CTA per window reads the (shifted) window straight from the frames with the
-// reference's flat-index addressing (PB:147-216), evaluates the circular cross-correlation with a
-// direct DFT in shared memory (one radix-2/4 split, O(w^3 / r)) (both frames packed into one complex transform, FP32, twiddles
-// from a table computed in FP64), subtracts the minimum (PB:518/724/796) and writes the fft-shifted
-// map to a scratch buffer; correlation_to_displacement (corr_to_disp_kernel, PB:346-422) and the
-// predictor glue (PB:728-738 / 800-810) follow as two small kernels.  Correct for every geometry,
-// roughly 15-30x slower per window than the fused kernels -- a completeness path, not the headline one.
+// reference's flat-index addressing (PB:147-216), evaluates the circular cross-correlation in shared
+// memory (both frames packed into ONE complex transform z = a + i b, FP32, twiddles from a table computed
+// in FP64), subtracts the minimum (PB:518/724/796) and writes the fft-shifted map to a scratch buffer;
+// correlation_to_displacement (corr_to_disp_kernel, PB:346-422) and the predictor glue (PB:728-738 /
+// 800-810) follow as two small kernels.
+//
+// The transform is a mixed-radix FFT (radices 8, 4, 2, 3, 5, 7, 11, 13) done IN PLACE without any reordering
+// pass: decimation in frequency forward (natural order in, digit-reversed order out), the spectrum product
+// P = conj(A^) B^ in the digit-reversed index space (partner bin -k through a small position table), and a
+// decimation-in-time transform back (digit-reversed in, natural out).  Work items are (line, butterfly)
+// pairs with the LINE index fastest across the lanes: every shared-memory access of a pass is then either
+// contiguous or strided by the odd row pitch, i.e. bank-conflict free for any window size.  Sizes with a
+// prime factor above 13 (22 = 2 x 11 is fine, 34 = 2 x 17 is not) fall back to direct sums (O(w^3 / r)).
 //
 // Included by pivb200.cu (needs corr_to_disp_kernel and grid_for).
 #pragma once
+#include "fft_regs.cuh"
 
 namespace pivb200 {
 
-constexpr int kGenericMaxWindow = 128;
-constexpr int kGenericThreads = 256;
+// cos / sin of 2 pi x for any x, at compile time (ct_cos2pi of fft_regs.cuh is for power-of-two denominators)
+__host__ __device__ constexpr double generic_ct_cos(double x) {
+    x = x - static_cast<double>(static_cast<long long>(x));
+    if (x < 0.0) x += 1.0;
+    if (x > 0.5) x = 1.0 - x;
+    bool neg = false;
+    if (x > 0.25) { x = 0.5 - x; neg = true; }
+    const double r = (x <= 0.125) ? ct_cos_small(2.0 * kPi * x) : ct_sin_small(2.0 * kPi * (0.25 - x));
+    return neg ? -r : r;
+}
+__host__ __device__ constexpr double generic_ct_sin(double x) { return generic_ct_cos(x - 0.25); }
+
+constexpr int kGenericMaxWindow = 160;           // bounded by shared memory: w (w + 1) complex values
+constexpr int kGenericThreads = 512;             // upper bound; generic_threads(w) picks the block size
+constexpr int kGenericMaxStages = 8;
 constexpr int kGenericShiftClamp = 1 << 20;          // same documented clamp as the fused kernels
 
 struct GenericParams {
@@ -39,31 +60,54 @@ struct GenericParams {
     float* corr_out;                       // [n_windows][w][w], fft-shifted
     float* win_a_out;                      // optional: the (shifted) windows themselves
     float* win_b_out;
+    int n_stages;                          // mixed-radix plan of the window size (0 = direct sums); generic_set_plan
+    int radix[kGenericMaxStages];
+    int blk[kGenericMaxStages];            // block size M of stage s (decimation in frequency order): w, w / R0, ...
+    FastDiv div_m[kGenericMaxStages];      // division by M / R
 };
 
-// one pixel of a shifted window, exactly like bilinear_cws_kernel / shift_dws_kernel above
-__device__ __forceinline__ float generic_fetch(const GenericParams& p, const unsigned char* frame, int gy, int gx,
-                                               bool cws, float vxf, float vyf, int vxi, int vyi) {
+// One pixel of a shifted window, exactly like bilinear_cws_kernel / shift_dws_kernel above.  The per-axis part
+// (PB:163-170: new = coord + v rounded in float32, floor / ceil taps, weights) is computed once per window column
+// and once per pixel row by the caller.
+struct GenericAxis {
+    int up, dn;         // ceil / floor tap (absolute pixel coordinate; |shift| is clamped to 2^20)
+    float w1, w0;       // (up - new), (new - down)
+};
+__device__ __forceinline__ GenericAxis generic_axis(int coord, float v) {
+    const float nw = __fadd_rn(static_cast<float>(coord), v);
+    const float upf = ceilf(nw), dnf = floorf(nw);
+    GenericAxis t;
+    t.up = static_cast<int>(upf);
+    t.dn = static_cast<int>(dnf);
+    t.w1 = __fsub_rn(upf, nw);
+    t.w0 = __fsub_rn(nw, dnf);
+    return t;
+}
+// flat index y * Wf + x clamped to the array ends (columns outside the frame wrap into the neighbouring rows,
+// PB:172-177 / 207-211); pixels inside the frame skip the 64-bit division
+__device__ __forceinline__ float generic_at(const GenericParams& p, const unsigned char* frame, int yy, int xx) {
+    if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.Wf) return static_cast<float>(frame[yy * p.pitch + xx]);
     const long long last = static_cast<long long>(p.H) * p.Wf - 1;
-    auto at = [&](long long q) {
-        q = q < 0 ? 0 : (q > last ? last : q);
-        const long long y = q / p.Wf, x = q - y * p.Wf;
-        return static_cast<float>(frame[y * p.pitch + x]);
-    };
-    if (!cws) return at(static_cast<long long>(gy + vyi) * p.Wf + (gx + vxi));
-    const float ny = __fadd_rn(static_cast<float>(gy), vyf);
-    const float nx = __fadd_rn(static_cast<float>(gx), vxf);
-    const float uxf = ceilf(nx), uyf = ceilf(ny), dxf = floorf(nx), dyf = floorf(ny);
-    const long long ux = static_cast<long long>(uxf), uy = static_cast<long long>(uyf);
-    const long long dx = static_cast<long long>(dxf), dy = static_cast<long long>(dyf);
-    const float q11 = at(dy * p.Wf + dx), q12 = at(uy * p.Wf + dx), q21 = at(dy * p.Wf + ux), q22 = at(uy * p.Wf + ux);
-    const float wx1 = __fsub_rn(uxf, nx), wx0 = __fsub_rn(nx, dxf);
-    const float wy1 = __fsub_rn(uyf, ny), wy0 = __fsub_rn(ny, dyf);
-    float acc = __fmul_rn(__fmul_rn(q11, wx1), wy1);
-    acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(q21, wx0), wy1));
-    acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(q12, wx1), wy0));
-    acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(q22, wx0), wy0));
-    return ((ux - dx) * (uy - dy) == 0) ? q11 : acc;
+    long long q = static_cast<long long>(yy) * p.Wf + xx;
+    q = q < 0 ? 0 : (q > last ? last : q);
+    const long long y = q / p.Wf, x = q - y * p.Wf;
+    return static_cast<float>(frame[y * p.pitch + x]);
+}
+__device__ __forceinline__ float generic_bilinear(const GenericParams& p, const unsigned char* frame, const GenericAxis& ay,
+                                                  const GenericAxis& ax) {
+    const float q11 = generic_at(p, frame, ay.dn, ax.dn), q12 = generic_at(p, frame, ay.up, ax.dn);
+    const float q21 = generic_at(p, frame, ay.dn, ax.up), q22 = generic_at(p, frame, ay.up, ax.up);
+    float acc = __fmul_rn(__fmul_rn(q11, ax.w1), ay.w1);
+    acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(q21, ax.w0), ay.w1));
+    acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(q12, ax.w1), ay.w0));
+    acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(q22, ax.w0), ay.w0));
+    // an exact-integer coordinate on either axis: all weights vanish, the value is the (floor y, floor x) tap (PB:170, 193)
+    return (ax.up == ax.dn || ay.up == ay.dn) ? q11 : acc;
+}
+
+__device__ __forceinline__ int generic_div(const FastDiv& d, int n) {
+    const uint32_t un = static_cast<uint32_t>(n), t = __umulhi(d.M, un);
+    return static_cast<int>((t + ((un - t) >> d.s1)) >> d.s2);
 }
 
 __device__ __forceinline__ float block_reduce(float v, float* red, int op) {   // op 0: sum, 1: min
@@ -77,7 +121,7 @@ __device__ __forceinline__ float block_reduce(float v, float* red, int op) {   /
     if (lane == 0) red[warp] = v;
     __syncthreads();
     float r = red[0];
-    for (int i = 1; i < kGenericThreads / 32; ++i) r = op ? fminf(r, red[i]) : r + red[i];
+    for (int i = 1; i < static_cast<int>(blockDim.x >> 5); ++i) r = op ? fminf(r, red[i]) : r + red[i];
     return r;
 }
 
@@ -96,7 +140,7 @@ __device__ __forceinline__ void generic_lines_r(float2* Z, const float2* tw, int
     const int es = columns ? pitch : 1, ls = columns ? 1 : pitch;
     const int m = w / R;
     const float sgn = conj ? -1.f : 1.f;
-    for (int L = warp; L < w; L += kGenericThreads / 32) {
+    for (int L = warp; L < w; L += static_cast<int>(blockDim.x >> 5)) {
         float2* line = Z + L * ls;
         float2 acc[R][J];
         int idx[J], stepk[J];
@@ -160,42 +204,209 @@ __device__ __forceinline__ void generic_lines_r(float2* Z, const float2* tw, int
     }
     __syncthreads();
 }
+// ----------------------------------------------------------------------------------------
+// Mixed-radix in-place FFT of every line of Z
+// ----------------------------------------------------------------------------------------
+// R-point DFT, forward sign (e^{-2 pi i t q / R}), natural order in and out
+template <int R>
+__device__ __forceinline__ void generic_small_dft(float2 (&v)[R]) {
+    auto add = [](float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); };
+    auto sub = [](float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); };
+    auto mul_mi = [](float2 a) { return make_float2(a.y, -a.x); };                  // * -i
+    if constexpr (R == 2) {
+        const float2 t = sub(v[0], v[1]);
+        v[0] = add(v[0], v[1]);
+        v[1] = t;
+    } else if constexpr (R == 4) {
+        const float2 t0 = add(v[0], v[2]), t1 = sub(v[0], v[2]), t2 = add(v[1], v[3]), t3 = mul_mi(sub(v[1], v[3]));
+        v[0] = add(t0, t2); v[2] = sub(t0, t2);
+        v[1] = add(t1, t3); v[3] = sub(t1, t3);
+    } else if constexpr (R == 8) {
+        float2 e[4] = {v[0], v[2], v[4], v[6]}, o[4] = {v[1], v[3], v[5], v[7]};
+        generic_small_dft<4>(e);
+        generic_small_dft<4>(o);
+        constexpr float h = 0.70710678118654752440f;
+        o[1] = make_float2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));           // * (1 - i) / sqrt 2
+        o[2] = mul_mi(o[2]);
+        o[3] = make_float2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));          // * (-1 - i) / sqrt 2
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { v[q] = add(e[q], o[q]); v[q + 4] = sub(e[q], o[q]); }
+    } else if constexpr (R == 16) {
+        float2 e[8], o[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { e[q] = v[2 * q]; o[q] = v[2 * q + 1]; }
+        generic_small_dft<8>(e);
+        generic_small_dft<8>(o);
+        static_for<1, 8>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            constexpr float c = float(generic_ct_cos(q / 16.0)), sn = float(generic_ct_sin(q / 16.0));
+            o[q] = make_float2(fmaf(o[q].x, c, o[q].y * sn), fmaf(o[q].y, c, -o[q].x * sn));      // * e^{-2 pi i q / 16}
+        });
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { v[q] = add(e[q], o[q]); v[q + 8] = sub(e[q], o[q]); }
+    } else {
+        // odd prime: out[q] = v0 + sum_t (c a_t -+ i s b_t) with a_t = v[t] + v[R-t], b_t = v[t] - v[R-t]
+        constexpr int Hh = (R - 1) / 2;
+        float2 a[Hh], b[Hh];
+#pragma unroll
+        for (int t = 1; t <= Hh; ++t) { a[t - 1] = add(v[t], v[R - t]); b[t - 1] = sub(v[t], v[R - t]); }
+        const float2 v0 = v[0];
+        float2 s0 = v0;
+#pragma unroll
+        for (int t = 0; t < Hh; ++t) s0 = add(s0, a[t]);
+        v[0] = s0;
+        static_for<1, Hh + 1>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            float re = v0.x, im = v0.y, xr = 0.f, xi = 0.f;
+            static_for<1, Hh + 1>([&](auto tc) {
+                constexpr int t = decltype(tc)::value;
+                constexpr float c = float(generic_ct_cos(double((t * q) % R) / R)), sn = float(generic_ct_sin(double((t * q) % R) / R));
+                re = fmaf(c, a[t - 1].x, re);
+                im = fmaf(c, a[t - 1].y, im);
+                xr = fmaf(sn, b[t - 1].y, xr);          // -i s b = (s b.y, -s b.x)
+                xi = fmaf(-sn, b[t - 1].x, xi);
+            });
+            v[q] = make_float2(re + xr, im + xi);
+            v[R - q] = make_float2(re - xr, im - xi);
+        });
+    }
+}
+
+// One in-place radix-R pass over all w lines (rows: elements Z[L][x]; columns: Z[x][L]).  Blocks of M elements,
+// butterflies over the R elements k + t M/R of a block; twiddles W_M^{t k} AFTER the butterfly (decimation in
+// frequency) or BEFORE it (decimation in time).  A warp takes butterfly j, its lanes take the lines L, L + 32, ...
+// `sub` is subtracted from every element as it is read (window means, first pass only).
+template <int R, bool DIT>
+__device__ __forceinline__ void generic_fft_pass(float2* Z, const float2* tw, int w, int pitch, bool columns, int M,
+                                                 const FastDiv& div_m, float2 sub) {
+    const int m = M / R, nb = w / R, tstep = (M == w) ? 1 : w / M;           // R is a compile-time constant: cheap divisions
+    const int es = columns ? pitch : 1, ls = columns ? 1 : pitch;
+    const int lane = threadIdx.x & 31, nwy = blockDim.x >> 5;
+    const int stride = m * es;
+    for (int j = threadIdx.x >> 5; j < nb; j += nwy) {
+        const int b = generic_div(div_m, j), k = j - b * m;
+        const int e0 = (b * M + k) * es;
+        for (int L = lane; L < w; L += 32) {
+            float2* base = Z + L * ls + e0;
+            float2 v[R];
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                v[q] = base[q * stride];
+                v[q].x -= sub.x;
+                v[q].y -= sub.y;
+            }
+            if constexpr (DIT) {
+                if (k != 0) {
+#pragma unroll
+                    for (int q = 1; q < R; ++q) v[q] = gmul(v[q], tw[q * k * tstep]);
+                }
+            }
+            generic_small_dft<R>(v);
+            if constexpr (!DIT) {
+                if (k != 0) {
+#pragma unroll
+                    for (int q = 1; q < R; ++q) v[q] = gmul(v[q], tw[q * k * tstep]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < R; ++q) base[q * stride] = v[q];
+        }
+    }
+    __syncthreads();
+}
+// BIG = false leaves out the radices 11, 13 and 16: the kernel for small windows then fits 64 registers
+template <bool DIT, bool BIG>
+__device__ __forceinline__ void generic_fft_pass_r(int R, float2* Z, const float2* tw, int w, int pitch, bool columns, int M,
+                                                   const FastDiv& div_m, float2 sub) {
+    if constexpr (BIG) {
+        if (R == 11) { generic_fft_pass<11, DIT>(Z, tw, w, pitch, columns, M, div_m, sub); return; }
+        if (R == 13) { generic_fft_pass<13, DIT>(Z, tw, w, pitch, columns, M, div_m, sub); return; }
+        if (R == 16) { generic_fft_pass<16, DIT>(Z, tw, w, pitch, columns, M, div_m, sub); return; }
+    }
+    switch (R) {
+        case 2: generic_fft_pass<2, DIT>(Z, tw, w, pitch, columns, M, div_m, sub); break;
+        case 3: generic_fft_pass<3, DIT>(Z, tw, w, pitch, columns, M, div_m, sub); break;
+        case 4: generic_fft_pass<4, DIT>(Z, tw, w, pitch, columns, M, div_m, sub); break;
+        case 5: generic_fft_pass<5, DIT>(Z, tw, w, pitch, columns, M, div_m, sub); break;
+        case 7: generic_fft_pass<7, DIT>(Z, tw, w, pitch, columns, M, div_m, sub); break;
+        default: generic_fft_pass<8, DIT>(Z, tw, w, pitch, columns, M, div_m, sub); break;
+    }
+}
+// forward transform of every line: natural order in, digit-reversed order out (bin k at generic_pos(k))
+template <bool BIG>
+__device__ __forceinline__ void generic_fft_dif(const GenericParams& p, float2* Z, const float2* tw, int w, int pitch, bool columns,
+                                                float2 sub) {
+    for (int s = 0; s < p.n_stages; ++s) {
+        generic_fft_pass_r<false, BIG>(p.radix[s], Z, tw, w, pitch, columns, p.blk[s], p.div_m[s], sub);
+        sub = make_float2(0.f, 0.f);
+    }
+}
+// forward transform of every line: digit-reversed order in, natural order out
+template <bool BIG>
+__device__ __forceinline__ void generic_fft_dit(const GenericParams& p, float2* Z, const float2* tw, int w, int pitch, bool columns) {
+    for (int s = p.n_stages - 1; s >= 0; --s)
+        generic_fft_pass_r<true, BIG>(p.radix[s], Z, tw, w, pitch, columns, p.blk[s], p.div_m[s], make_float2(0.f, 0.f));
+}
+// where generic_fft_dif leaves bin k
+__device__ __forceinline__ int generic_pos(const GenericParams& p, int k, int w) {
+    int pos = 0, rem = k, M = w;
+    for (int s = 0; s < p.n_stages; ++s) {
+        const int R = p.radix[s];
+        const int nxt = rem / R;
+        const int q = rem - nxt * R;
+        rem = nxt;
+        M /= R;
+        pos += q * M;
+    }
+    return pos;
+}
+
 __device__ __forceinline__ void generic_lines(float2* Z, const float2* tw, int w, int pitch, bool columns, bool conj) {
     if (w % 4 == 0 && w >= 96) generic_lines_r<4>(Z, tw, w, pitch, columns, conj);
     else if (w >= 16) generic_lines_r<2>(Z, tw, w, pitch, columns, conj);
     else generic_lines_r<1>(Z, tw, w, pitch, columns, conj);
 }
 
-__global__ void __launch_bounds__(kGenericThreads) generic_corr_kernel(const GenericParams p) {
+template <bool BIG>
+__global__ void __launch_bounds__(BIG ? kGenericThreads : 256, BIG ? 1 : 4) generic_corr_kernel(const GenericParams p) {
     extern __shared__ __align__(16) unsigned char gsm[];
     const int w = p.wind, pitch = w + 1, half = w / 2;
     float2* Z = reinterpret_cast<float2*>(gsm);
     float2* tw = Z + w * pitch;
     float* red = reinterpret_cast<float*>(tw + w);
+    unsigned short* pos_of = reinterpret_cast<unsigned short*>(red + 64);     // bin k -> position (digit reversal)
+    unsigned short* bin_at = pos_of + w;                                      // position -> bin
+    const bool fft = p.n_stages > 0;
     for (int k = threadIdx.x; k < w; k += blockDim.x) {
         double s, c;
         sincospi(2.0 * k / w, &s, &c);
         tw[k] = make_float2(static_cast<float>(c), static_cast<float>(-s));      // e^{-2 pi i k / w}
+        const int q = fft ? generic_pos(p, k, w) : k;
+        pos_of[k] = static_cast<unsigned short>(q);
+        bin_at[q] = static_cast<unsigned short>(k);
     }
     __syncthreads();
     const int per_pair = p.n_rows * p.n_cols;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, nwy = blockDim.x >> 5;
     for (long long wq = blockIdx.x; wq < p.n_windows; wq += gridDim.x) {
         const long long g = p.first_window + wq;
-        // ---- the two windows, packed as z = a + i b -------------------------------------------
+        // ---- the two windows, packed as z = a + i b (a warp takes rows, its lanes take columns) ----
         float sum_a = 0.f, sum_b = 0.f;
         if (p.wa != nullptr) {
-            for (int e = threadIdx.x; e < w * w; e += blockDim.x) {
-                const long long q = g * w * w + e;
-                const float a = p.explicit_dtype ? static_cast<float>(static_cast<const unsigned char*>(p.wa)[q])
-                                                 : static_cast<const float*>(p.wa)[q];
-                const float b = p.explicit_dtype ? static_cast<float>(static_cast<const unsigned char*>(p.wb)[q])
-                                                 : static_cast<const float*>(p.wb)[q];
-                Z[(e / w) * pitch + e % w] = make_float2(a, b);
-            }
+            for (int i = ty; i < w; i += nwy)
+                for (int j = tx; j < w; j += 32) {
+                    const long long q = g * w * w + i * w + j;
+                    const float a = p.explicit_dtype ? static_cast<float>(static_cast<const unsigned char*>(p.wa)[q])
+                                                     : static_cast<const float*>(p.wa)[q];
+                    const float b = p.explicit_dtype ? static_cast<float>(static_cast<const unsigned char*>(p.wb)[q])
+                                                     : static_cast<const float*>(p.wb)[q];
+                    Z[i * pitch + j] = make_float2(a, b);
+                }
         } else {
             const long long pair = g / per_pair;
             const int loc = static_cast<int>(g - pair * per_pair);
-            const int r0 = (loc / p.n_cols) * p.step, c0 = (loc % p.n_cols) * p.step;
+            const int wr = loc / p.n_cols;
+            const int r0 = wr * p.step, c0 = (loc - wr * p.n_cols) * p.step;
             const unsigned char* fa = p.fa + pair * p.pair_stride;
             const unsigned char* fb = p.fb + pair * p.pair_stride;
             const bool cws = (p.mode == PIVB200_MODE_CWS) && p.sxf != nullptr;
@@ -209,69 +420,104 @@ __global__ void __launch_bounds__(kGenericThreads) generic_corr_kernel(const Gen
                 vxi = max(-kGenericShiftClamp, min(kGenericShiftClamp, p.sxi[g]));
                 vyi = max(-kGenericShiftClamp, min(kGenericShiftClamp, p.syi[g]));
             }
-            for (int e = threadIdx.x; e < w * w; e += blockDim.x) {
-                const int i = e / w, j = e - i * w;
-                // frame a is shifted by -s, frame b by +s (PB:720-723 / 792-795)
-                const float a = generic_fetch(p, fa, r0 + i, c0 + j, cws, -vxf, -vyf, -vxi, -vyi);
-                const float b = generic_fetch(p, fb, r0 + i, c0 + j, cws, vxf, vyf, vxi, vyi);
-                Z[i * pitch + j] = make_float2(a, b);
-                sum_a += a;
-                sum_b += b;
-                if (p.win_a_out) {
-                    p.win_a_out[g * w * w + e] = a;
-                    p.win_b_out[g * w * w + e] = b;
+            // a lane keeps its column(s): the x-axis taps are computed once per column, the y-axis taps once per pixel row;
+            // frame a is shifted by -s, frame b by +s (PB:720-723 / 792-795)
+            for (int j = tx; j < w; j += 32) {
+                GenericAxis xa, xb;
+                if (cws) { xa = generic_axis(c0 + j, -vxf); xb = generic_axis(c0 + j, vxf); }
+                for (int i = ty; i < w; i += nwy) {
+                    float a, b;
+                    if (cws) {
+                        a = generic_bilinear(p, fa, generic_axis(r0 + i, -vyf), xa);
+                        b = generic_bilinear(p, fb, generic_axis(r0 + i, vyf), xb);
+                    } else {
+                        a = generic_at(p, fa, r0 + i - vyi, c0 + j - vxi);
+                        b = generic_at(p, fb, r0 + i + vyi, c0 + j + vxi);
+                    }
+                    Z[i * pitch + j] = make_float2(a, b);
+                    sum_a += a;
+                    sum_b += b;
+                    if (p.win_a_out) {
+                        p.win_a_out[g * w * w + i * w + j] = a;
+                        p.win_b_out[g * w * w + i * w + j] = b;
+                    }
                 }
             }
         }
         if (p.corr_out == nullptr) { __syncthreads(); continue; }         // windows only
+        // Pass mode.  The window means are removed before the transform: subtracting a mean shifts every
+        // correlation value by the same constant, which `- amin` removes anyway, and the FP32 map keeps ~4 more
+        // significant bits (same reason the fused kernels drop the DC bin).  Pass 1 additionally divides by the
+        // means (PB:513-514): a factor 1 / (mean a * mean b) on the whole map, applied when the map is written
+        // (0 / 0 = NaN for a black window, like the reference).
+        float2 means = make_float2(0.f, 0.f);
+        float norm = 1.0f;
         if (p.subtract_min && p.wa == nullptr) {
-            // Pass mode.  The window means are removed before the transform: subtracting a mean shifts every
-            // correlation value by the same constant, which `- amin` removes anyway, and the FP32 map
-            // keeps ~4 more significant bits (same reason the fused kernels drop the DC bin).  Pass 1
-            // additionally divides by the mean (PB:513-514).
-            const float ma = block_reduce(sum_a, red, 0) / static_cast<float>(w * w);
-            const float mb = block_reduce(sum_b, red, 0) / static_cast<float>(w * w);
-            for (int e = threadIdx.x; e < w * w; e += blockDim.x) {
-                float2& z = Z[(e / w) * pitch + e % w];
-                z = make_float2(z.x - ma, z.y - mb);
-                if (p.normalize) z = make_float2(z.x / ma, z.y / mb);     // 0 / 0 = NaN like the reference
+            means.x = block_reduce(sum_a, red, 0) / static_cast<float>(w * w);
+            means.y = block_reduce(sum_b, red, 0) / static_cast<float>(w * w);
+            if (p.normalize) norm = (1.0f / means.x) * (1.0f / means.y);
+            if (!fft) {
+                for (int i = ty; i < w; i += nwy)
+                    for (int j = tx; j < w; j += 32) {
+                        float2& z = Z[i * pitch + j];
+                        z = make_float2(z.x - means.x, z.y - means.y);
+                    }
             }
         }
         __syncthreads();
         // ---- Z^ = DFT2(a + i b) ----------------------------------------------------------------
-        generic_lines(Z, tw, w, pitch, false, false);
-        generic_lines(Z, tw, w, pitch, true, false);
+        if (fft) {
+            generic_fft_dif<BIG>(p, Z, tw, w, pitch, false, means);      // the means are subtracted as the first pass reads
+            generic_fft_dif<BIG>(p, Z, tw, w, pitch, true, make_float2(0.f, 0.f));
+        } else {
+            generic_lines(Z, tw, w, pitch, false, false);
+            generic_lines(Z, tw, w, pitch, true, false);
+        }
         // ---- P = conj(A^) B^ with A^ = (Z^[k] + conj Z^[-k]) / 2, B^ = (Z^[k] - conj Z^[-k]) / 2i -----
-        for (int e = threadIdx.x; e < w * w; e += blockDim.x) {
-            const int ky = e / w, kx = e - ky * w;
-            const int ny = ky ? w - ky : 0, nx = kx ? w - kx : 0;
-            const int en = ny * w + nx;
-            if (e > en) continue;                                          // the partner's thread does both
-            const float2 zk = Z[ky * pitch + kx], zn = Z[ny * pitch + nx];
-            const float2 A = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-            const float2 B = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
-            const float2 P = make_float2(fmaf(A.x, B.x, A.y * B.y), fmaf(A.x, B.y, -A.y * B.x));
-            Z[ky * pitch + kx] = P;
-            if (en != e) Z[ny * pitch + nx] = make_float2(P.x, -P.y);
+        // (py, px) = position of bin (ky, kx), (qy, qx) = position of its partner (-ky, -kx).  The FFT path
+        // stores conj(P): the map is real, so the inverse transform is the FORWARD transform of conj(P).
+        for (int py = ty; py < w; py += nwy) {
+            const int ky = bin_at[py];
+            const int qy = pos_of[ky ? w - ky : 0];
+            for (int px = tx; px < w; px += 32) {
+                const int kx = bin_at[px];
+                const int qx = pos_of[kx ? w - kx : 0];
+                const int e = py * w + px, en = qy * w + qx;
+                if (e > en) continue;                                      // the partner's thread does both
+                const float2 zk = Z[py * pitch + px], zn = Z[qy * pitch + qx];
+                const float2 A = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+                const float2 B = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+                const float2 P = make_float2(fmaf(A.x, B.x, A.y * B.y), fmaf(A.x, B.y, -A.y * B.x));
+                Z[py * pitch + px] = fft ? make_float2(P.x, -P.y) : P;
+                if (en != e) Z[qy * pitch + qx] = fft ? P : make_float2(P.x, -P.y);
+            }
         }
         __syncthreads();
         // ---- inverse transform (real result) ---------------------------------------------------
-        generic_lines(Z, tw, w, pitch, true, true);
-        generic_lines(Z, tw, w, pitch, false, true);
-        const float scale = 1.0f / (static_cast<float>(w) * static_cast<float>(w));
+        if (fft) {
+            generic_fft_dit<BIG>(p, Z, tw, w, pitch, true);
+            generic_fft_dit<BIG>(p, Z, tw, w, pitch, false);
+        } else {
+            generic_lines(Z, tw, w, pitch, true, true);
+            generic_lines(Z, tw, w, pitch, false, true);
+        }
+        const float scale = norm / (static_cast<float>(w) * static_cast<float>(w));
         float mn = 0.f;
         if (p.subtract_min) {
             float m = FLT_MAX;
-            for (int e = threadIdx.x; e < w * w; e += blockDim.x) m = fminf(m, Z[(e / w) * pitch + e % w].x * scale);
+            for (int i = ty; i < w; i += nwy)
+                for (int j = tx; j < w; j += 32) m = fminf(m, Z[i * pitch + j].x * scale);
             mn = block_reduce(m, red, 1);
         }
         float* out = p.corr_out + wq * w * w;
-        for (int e = threadIdx.x; e < w * w; e += blockDim.x) {
-            const int i = e / w, j = e - i * w;                             // position in the fft-shifted map
-            const int si = i >= half ? i - half : i + half, sj = j >= half ? j - half : j + half;
-            float val = Z[si * pitch + sj].x * scale;
-            // NaN maps (black window divided by its zero mean) stay NaN: fminf drops NaNs, the subtraction keeps them
-            out[e] = p.subtract_min ? val - mn : val;
+        for (int i = ty; i < w; i += nwy) {
+            const int si = i >= half ? i - half : i + half;              // (i, j) = position in the fft-shifted map
+            for (int j = tx; j < w; j += 32) {
+                const int sj = j >= half ? j - half : j + half;
+                const float val = Z[si * pitch + sj].x * scale;
+                // NaN maps (black window divided by its zero mean) stay NaN: fminf drops NaNs, the subtraction keeps them
+                out[i * w + j] = p.subtract_min ? val - mn : val;
+            }
         }
         __syncthreads();
     }
@@ -301,21 +547,52 @@ __global__ void generic_glue_kernel(const double* __restrict__ du, const double*
 inline bool generic_window_ok(int wind) { return wind >= 4 && wind <= kGenericMaxWindow && wind % 2 == 0; }
 
 inline size_t generic_smem_bytes(int w) {
-    return static_cast<size_t>(w) * (w + 1) * sizeof(float2) + static_cast<size_t>(w) * sizeof(float2) + 64 * sizeof(float);
+    return static_cast<size_t>(w) * (w + 1) * sizeof(float2) + static_cast<size_t>(w) * sizeof(float2) + 64 * sizeof(float) +
+           2 * static_cast<size_t>(w) * sizeof(unsigned short);
 }
 
-inline int generic_launch(const GenericParams& gp, cudaStream_t s) {
+// threads per window: small windows are latency-bound by their ~25 block-wide phases, so they get small blocks
+// and many resident blocks per SM; a 128 px window has 16 K pixels and one block per SM (shared memory)
+inline int generic_threads(int w) {
+    if (const char* e = getenv("PIVB200_GENERIC_THREADS")) { const int t = atoi(e); if (t >= 32 && t <= kGenericThreads && t % 32 == 0) return t; }
+    const int px = w * w;
+    return px <= 1024 ? 64 : (px <= 4096 ? 128 : (px <= 9216 ? 256 : kGenericThreads));
+}
+
+// radices of the window size (8, 4, 2 first, then the odd primes up to 13); n_stages = 0 -> direct sums
+inline void generic_set_plan(GenericParams& gp) {
+    static const int kRadices[] = {16, 8, 4, 2, 3, 5, 7, 11, 13};
+    int n = gp.wind, ns = 0;
+    const bool small = generic_threads(gp.wind) <= 256;       // small windows: no radix 16 (64-register kernel)
+    for (int r : kRadices)
+        while (n % r == 0 && ns < kGenericMaxStages && !(small && r == 16)) {
+            gp.radix[ns] = r;
+            gp.blk[ns] = n;
+            gp.div_m[ns] = make_fastdiv(static_cast<uint32_t>(n / r));
+            ++ns;
+            n /= r;
+        }
+    gp.n_stages = (n == 1) ? ns : 0;
+    if (const char* e = getenv("PIVB200_GENERIC_DIRECT")) if (atoi(e)) gp.n_stages = 0;      // A/B switch: direct sums
+}
+
+inline int generic_launch(const GenericParams& gp_in, cudaStream_t s) {
+    GenericParams gp = gp_in;
+    generic_set_plan(gp);
     const size_t smem = generic_smem_bytes(gp.wind);
-    cudaError_t err = cudaFuncSetAttribute(generic_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(smem));
+    const int threads = generic_threads(gp.wind);
+    bool big = threads > 256;
+    for (int i = 0; i < gp.n_stages; ++i) big = big || gp.radix[i] > 8;
+    auto kern = big ? generic_corr_kernel<true> : generic_corr_kernel<false>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (err != cudaSuccess) return static_cast<int>(err);
     int dev = 0, sms = 0, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, generic_corr_kernel, kGenericThreads, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
     long long grid = static_cast<long long>(sms) * (per_sm > 0 ? per_sm : 1);
     if (grid > gp.n_windows) grid = gp.n_windows;
-    generic_corr_kernel<<<static_cast<unsigned>(grid), kGenericThreads, smem, s>>>(gp);
+    kern<<<static_cast<unsigned>(grid), threads, smem, s>>>(gp);
     count_launch();
     return static_cast<int>(cudaGetLastError());
 }
