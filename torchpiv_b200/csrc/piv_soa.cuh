@@ -135,8 +135,85 @@ struct SmemS {
     static constexpr int BY_SMEM = SMEM_MAX / STRIDE;
     static constexpr int NWARPS0 = BY_SMEM < WARP_CAP ? BY_SMEM : WARP_CAP;
     static constexpr int NWARPS = NWARPS0 < TMEM_CAP ? NWARPS0 : TMEM_CAP;
-    static constexpr int CTA_BYTES = NWARPS * STRIDE;
+    // peak records waiting for the scalar tail of the epilogue (soa_flush_tail): QN records of 40 bytes per warp,
+    // behind the warp slots
+    static constexpr int QN = (W == 16) ? 8 : 16;
+    static constexpr int QREC = 40;
+    static constexpr int Q_OFF = NWARPS * STRIDE;
+    static constexpr int CTA_BYTES = Q_OFF + NWARPS * QN * QREC;
+    static_assert(QN % G::NW == 0, "whole jobs per flush");
+    static_assert(CTA_BYTES <= SMEM_MAX, "shared memory");
 };
+
+// What the map-dependent part of the epilogue leaves per window; everything else (sub-pixel fit, ratio test,
+// predictor replacement, stores: PB:394-422, 728-738) is scalar work that soa_flush_tail does for QN windows at once,
+// one window per lane, instead of once per job with all lanes of a window computing the same numbers.
+struct PeakRec {
+    int g;              // global window index, -1 = padding
+    int m;              // flat index of the peak in the fft-shifted map
+    float cm0;          // peak - min
+    float fl, fr, ft, fb;   // flat neighbours m+1, m-1, m+W, m-W (guarded, PB:385-392), each minus min
+    float spd;          // second peak - min
+    float sa, sb;       // pixel sums of the two windows
+};
+static_assert(sizeof(PeakRec) == 40, "PeakRec layout");
+
+template <int W>
+__device__ __noinline__ void soa_flush_tail(const PassParams& p, const PeakRec* q, int count, int lane) {
+    using G = GeoS<W>;
+    constexpr int H = G::H, LOGW = G::LOGW, N2 = W * W;
+    if (lane < count) {
+        const PeakRec r = q[lane];
+        const int g = r.g;
+        if (g >= 0) {
+            // eps of PB:381 in the map's scale; pass 1 divides the frames by their means (PB:513-514), which scales eps
+            float eps = G::K * 1e-7f;
+            if (p.first_pass) eps *= (r.sa * (1.0f / N2)) * (r.sb * (1.0f / N2));
+            // Three-point log-Gaussian fit (PB:394-407) in FP32 on RATIOS to the peak value:
+            //   (ln c- - ln c+) / (2 ln c+ + 2 ln c- - 4 ln c0) = (B - A) / (2 (A + B)),  A = ln(c+ / c0), B = ln(c- / c0),
+            // which needs no FP64: the differences of logarithms are formed directly instead of by cancellation.
+            // Agreement with the FP64 evaluation of the reference: ~1e-7 px, below what the FP32 rounding of the map
+            // itself contributes.  IEEE division: c / c == 1 exactly (featureless windows).
+            const float cm = r.cm0 + eps;
+            const float ll = logf((r.fl + eps) / cm), lr = logf((r.fr + eps) / cm);
+            const float lt = logf((r.ft + eps) / cm), lb = logf((r.fb + eps) / cm);
+            const float fu = (lr - ll) / (2.0f * (ll + lr)), fv = (lb - lt) / (2.0f * (lb + lt));
+            const int R = r.m >> LOGW, C = r.m & (W - 1);
+            // torch.nan_to_num (PB:418-419)
+            double du = isnan(fu) ? 0.0 : (isinf(fu) ? copysign(DBL_MAX, static_cast<double>(fu))
+                                                     : static_cast<double>(C - H) + static_cast<double>(fu));
+            double dv = isnan(fv) ? 0.0 : (isinf(fv) ? copysign(DBL_MAX, static_cast<double>(fv))
+                                                     : static_cast<double>(R - H) + static_cast<double>(fv));
+            bool invalid = false;
+            float ratio = 0.f;
+            if (p.validate) {
+                ratio = cm / (r.spd + eps);
+                invalid = static_cast<double>(ratio) < p.val_ratio;
+            }
+            if (p.first_pass && (r.sa == 0.f || r.sb == 0.f)) {
+                // black window: the reference divides by a zero mean (PB:513-514), every value is NaN,
+                // nan_to_num gives 0 and the NaN ratio compares False (valid)
+                du = dv = 0.0;
+                invalid = false;
+                ratio = 0.f;
+            }
+            double uo = du, vo = dv;
+            if (p.base_u) { uo += p.base_u[g]; vo += p.base_v[g]; }
+            if (p.pred_u) {
+                // PB:731-738: reject where the correction exceeds a positive predictor, or invalid
+                const double pred_u = p.pred_u[g], pred_v = p.pred_v[g];
+                if ((du > pred_u && rint(pred_u) > 0.0) || invalid) uo = pred_u;
+                if ((dv > pred_v && rint(pred_v) > 0.0) || invalid) vo = pred_v;
+            }
+            p.u[g] = uo;
+            p.v[g] = vo;
+            if (p.mask) p.mask[g] = invalid ? 1 : 0;
+            if (p.ratio) p.ratio[g] = ratio;
+        }
+    }
+    __syncwarp();
+}
+
 
 // Request the tiles of `frame` of the warp's current job (TileDesc table in shared memory): TMA for the windows that
 // overlap the frame, byte gather for the rest.  The mbarrier is armed for EVERY (job, frame), also with nothing to
@@ -153,24 +230,23 @@ __device__ __noinline__ void stage_tiles(const CUtensorMap* tmA, const CUtensorM
     const uint32_t bar = smem_u32(smem + S::BAR_OFF);
     fence_proxy_async();            // generic accesses to the buffers are ordered before the TMA writes
     __syncwarp();
-    uint32_t tx = 0;
+    // lane w2 < NW owns window w2 of the job
+    const int w2 = lane & (NW - 1);
+    const bool mine = lane < NW;
+    const TileDesc dsc = desc[w2 * 2 + frame];
+    const unsigned by_tma = __ballot_sync(0xffffffffu, mine && dsc.d >= 0);
+    const unsigned by_gather = __ballot_sync(0xffffffffu, mine && dsc.d < 0);
+    if (by_gather) {                // windows entirely outside the frame (rare): the whole warp gathers them
 #pragma unroll 1
-    for (int w2 = 0; w2 < NW; ++w2) {
-        const TileDesc dsc = desc[w2 * 2 + frame];
-        if (dsc.d >= 0) tx += T::TX;
-        else gather_border_tile<W, LOADER>(p, dsc, smem + S::REG_OFF + w2 * G::REGION, frame, lane);
+        for (int w3 = 0; w3 < NW; ++w3)
+            if ((by_gather >> w3) & 1)
+                gather_border_tile<W, LOADER>(p, desc[w3 * 2 + frame], smem + S::REG_OFF + w3 * G::REGION, frame, lane);
     }
-    if (lane == 0) {
-        mbar_arrive_expect_tx(bar, tx);
-#pragma unroll 1
-        for (int w2 = 0; w2 < NW; ++w2) {
-            const TileDesc dsc = desc[w2 * 2 + frame];
-            if (dsc.d >= 0)
-                tma_load_3d(smem_u32(smem + S::REG_OFF + w2 * G::REGION), frame ? tmB : tmA, bar, dsc.ox & ~15, dsc.oy, dsc.pair);
-        }
-    }
+    if (lane == 0) mbar_arrive_expect_tx(bar, static_cast<uint32_t>(__popc(by_tma)) * T::TX);
     __syncwarp();
-    if (lane < NW && desc[lane * 2 + frame].d < 0) desc[lane * 2 + frame].d = 0;     // gathered tiles start at byte 0
+    if (mine && dsc.d >= 0)
+        tma_load_3d(smem_u32(smem + S::REG_OFF + w2 * G::REGION), frame ? tmB : tmA, bar, dsc.ox & ~15, dsc.oy, dsc.pair);
+    if (mine && dsc.d < 0) desc[w2 * 2 + frame].d = 0;     // gathered tiles start at byte 0
     __syncwarp();
 }
 
@@ -247,6 +323,8 @@ __global__ void __launch_bounds__(SmemS<W, LOADER>::NWARPS * 32, 1) piv_soa_kern
             else asm volatile("bar.sync %0, %1;" ::"r"(1 + warp / p.sync_group), "r"(p.sync_group * 32) : "memory");
         }
     };
+    PeakRec* const queue = reinterpret_cast<PeakRec*>(smem_cta + S::Q_OFF + warp * (S::QN * S::QREC));
+    int queued = 0;
     bool prefetched = false;
 #pragma unroll 1
     for (int base = blockIdx.x * nwarps; base < njobs; base += job_stride) {
@@ -504,15 +582,11 @@ __global__ void __launch_bounds__(SmemS<W, LOADER>::NWARPS * 32, 1) piv_soa_kern
         });
         __syncwarp();
 
-        // =============================== epilogue (PB:360-422, 728-738) ==========================
+        // =============================== epilogue (PB:360-422) ===================================
+        // Here: everything that needs the map.  The scalar rest happens in soa_flush_tail, QN windows at a time.
         lockstep(5);
         {
             auto at2 = [&](int R, int C) { return mapw[((R >> 1) * PM + C) * 2 + (R & 1)]; };
-            double base_u = 0.0, base_v = 0.0, pred_u = 0.0, pred_v = 0.0;
-            if (l == 0 && g_valid) {
-                if (p.base_u) { base_u = p.base_u[g]; base_v = p.base_v[g]; }
-                if (p.pred_u) { pred_u = p.pred_u[g]; pred_v = p.pred_v[g]; }
-            }
             const float gmax = group_max<H>(fmaxf(mx0, mx1)), gmin = group_min<H>(mn);
             // first maximum in flat (row-major) order of the shifted map (torch argmax, PB:383)
             constexpr int BIG = 1 << 20;
@@ -523,39 +597,56 @@ __global__ void __launch_bounds__(SmemS<W, LOADER>::NWARPS * 32, 1) piv_soa_kern
             constexpr int N2 = W * W;
             const int m = R * W + C;
             auto at = [&](int f) { return at2(f >> LOGW, f & (W - 1)); };
-            // flat neighbours, guarded only at the array ends (PB:385-392)
+            // flat neighbours, guarded only at the array ends (PB:385-392); lanes 1..4 of the window fetch one each
             const int il = (m + 1 >= N2 - 1) ? m : m + 1;
             const int ir = (m - 1 <= 0) ? m : m - 1;
             const int it_ = (m + W >= N2 - 1) ? m : m + W;
             const int ib = (m - W <= 0) ? m : m - W;
-            // eps of PB:381 in the map's scale; pass 1 divides the frames by their means (PB:513-514), which scales eps
-            float eps = G::K * 1e-7f;
-            const float sa = __shfl_sync(FULL, sum_a, wi * H), sb = __shfl_sync(FULL, sum_b, wi * H);
-            if (p.first_pass) eps *= (sa * (1.0f / N2)) * (sb * (1.0f / N2));
-            const float f_l = at(il), f_r = at(ir), f_t = at(it_), f_b = at(ib);
+            const float fsel = at((l == 1) ? il : (l == 2) ? ir : (l == 3) ? it_ : ib) - gmin;
             // second peak: maximum outside the 7x7 flat-index patch around m, each patch index clamped to
-            // [0, N2-1] (PB:346-358).  Rows that cannot touch the patch reuse the row maxima from registers.
+            // [0, N2-1] (PB:346-358).  Rows that cannot touch the patch reuse the row maxima from registers; the up to
+            // eight rows that can are read back, two columns per lane.  Element (rr, cc) has the patch coordinate
+            // e = rr W + cc - lo_f: its column part (e mod W) depends on cc only, its row part is rr + ((cc - lo_f) >> LOGW).
             float sp = -FLT_MAX;
             if (p.validate) {
                 const int lo_f = m - 3 - 3 * W, hi_f = m + 3 + 3 * W;
                 const int ra = max(lo_f, 0) >> LOGW, rb = min(hi_f, N2 - 1) >> LOGW;
                 if (sr0 < ra || sr0 > rb) sp = fmaxf(sp, mx0);
                 if (sr0 + 1 < ra || sr0 + 1 > rb) sp = fmaxf(sp, mx1);
-                for (int rr = ra; rr <= rb; ++rr) {
+                const int d0 = l - lo_f, d1 = l + H - lo_f;
+                const bool col0 = (d0 & (W - 1)) <= 6, col1 = (d1 & (W - 1)) <= 6;
+                const int ro0 = d0 >> LOGW, ro1 = d1 >> LOGW;
+                // the clamped ends: index 0 belongs to the patch when the patch reaches below 0, N2-1 when beyond the end
+                const bool z0 = (lo_f <= 0) && (l == 0), zN = (hi_f >= N2 - 1) && (l == H - 1);
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int cc = l + h * H;
-                        const int f = rr * W + cc;
-                        const int e = f - lo_f;                     // (i+3) + W (j+3)
-                        bool in_patch = (e >= 0) && ((e & (W - 1)) <= 6) && ((e >> LOGW) <= 6);
-                        in_patch |= (f == 0 && lo_f <= 0) || (f == N2 - 1 && hi_f >= N2 - 1);
-                        if (!in_patch) sp = fmaxf(sp, at2(rr, cc));
+                for (int t = 0; t < 8; ++t) {
+                    const int rr = ra + t;
+                    if (rr <= rb) {
+                        const float* row = mapw + (rr >> 1) * (2 * PM) + (rr & 1);
+                        const bool in0 = (col0 && static_cast<unsigned>(rr + ro0) <= 6u) || (t == 0 && z0);
+                        const bool in1 = (col1 && static_cast<unsigned>(rr + ro1) <= 6u) || (rr == rb && zN);
+                        const float v0 = row[2 * l], v1 = row[2 * (l + H)];
+                        sp = fmaxf(sp, in0 ? -FLT_MAX : v0);
+                        sp = fmaxf(sp, in1 ? -FLT_MAX : v1);
                     }
                 }
                 sp = group_max<H>(sp);
             }
-            // The map has been read for the last time: the next job's descriptors and frame-a tiles are requested
-            // now, so the TMA runs underneath the FP64 fit below.
+            const int l0 = wi * H;
+            const float f_l = __shfl_sync(FULL, fsel, l0 + 1), f_r = __shfl_sync(FULL, fsel, l0 + 2),
+                        f_t = __shfl_sync(FULL, fsel, l0 + 3), f_b = __shfl_sync(FULL, fsel, l0 + 4);
+            if (l == 0) {
+                PeakRec rec;
+                rec.g = g_valid ? g : -1;
+                rec.m = m;
+                rec.cm0 = gmax - gmin;
+                rec.fl = f_l; rec.fr = f_r; rec.ft = f_t; rec.fb = f_b;
+                rec.spd = sp - gmin;
+                rec.sa = sum_a; rec.sb = sum_b;
+                queue[queued + wi] = rec;
+            }
+            queued += NW;
+            // The map has been read for the last time: the next job's descriptors and frame-a tiles are requested now
             __syncwarp();
             prefetched = false;
             if (base + job_stride < njobs) {
@@ -563,53 +654,13 @@ __global__ void __launch_bounds__(SmemS<W, LOADER>::NWARPS * 32, 1) piv_soa_kern
                 stage_issue(0);
                 prefetched = true;
             }
-            // Three-point log-Gaussian fit (PB:394-407) in FP32 on RATIOS to the peak value:
-            //   (ln c- - ln c+) / (2 ln c+ + 2 ln c- - 4 ln c0) = (B - A) / (2 (A + B)),  A = ln(c+ / c0), B = ln(c- / c0),
-            // which needs no FP64: the differences of logarithms are formed directly instead of by cancellation.
-            // The four logarithms are evaluated by four lanes of the window.  Agreement with the FP64 evaluation of
-            // the reference: ~1e-7 px, below what the FP32 rounding of the map itself contributes.
-            const float cm = (gmax - gmin) + eps;
-            const float csel = ((l == 1) ? f_l : (l == 2) ? f_r : (l == 3) ? f_t : f_b) - gmin + eps;
-            const float lg = logf(csel / cm);               // IEEE division: c / c == 1 exactly (featureless windows)
-            const int l0 = wi * H;
-            const float ll = __shfl_sync(FULL, lg, l0 + 1), lr = __shfl_sync(FULL, lg, l0 + 2),
-                        lt = __shfl_sync(FULL, lg, l0 + 3), lb = __shfl_sync(FULL, lg, l0 + 4);
-            const float fu = (lr - ll) / (2.0f * (ll + lr)), fv = (lb - lt) / (2.0f * (lb + lt));
-            // torch.nan_to_num (PB:418-419)
-            double du = isnan(fu) ? 0.0 : (isinf(fu) ? copysign(DBL_MAX, static_cast<double>(fu))
-                                                     : static_cast<double>(C - H) + static_cast<double>(fu));
-            double dv = isnan(fv) ? 0.0 : (isinf(fv) ? copysign(DBL_MAX, static_cast<double>(fv))
-                                                     : static_cast<double>(R - H) + static_cast<double>(fv));
-
-            bool invalid = false;
-            float ratio = 0.f;
-            if (p.validate) {
-                ratio = cm / ((sp - gmin) + eps);
-                invalid = static_cast<double>(ratio) < p.val_ratio;
+            if (queued == S::QN) {
+                soa_flush_tail<W>(p, queue, queued, lane);
+                queued = 0;
             }
-            if (p.first_pass && (sa == 0.f || sb == 0.f)) {
-                // black window: the reference divides by a zero mean (PB:513-514), every value is NaN,
-                // nan_to_num gives 0 and the NaN ratio compares False (valid)
-                du = dv = 0.0;
-                invalid = false;
-                ratio = 0.f;
-            }
-            if (l == 0 && g_valid) {
-                double uo = du + base_u;
-                double vo = dv + base_v;
-                if (p.pred_u) {
-                    // PB:731-738: reject where the correction exceeds a positive predictor, or invalid
-                    if ((du > pred_u && rint(pred_u) > 0.0) || invalid) uo = pred_u;
-                    if ((dv > pred_v && rint(pred_v) > 0.0) || invalid) vo = pred_v;
-                }
-                p.u[g] = uo;
-                p.v[g] = vo;
-                if (p.mask) p.mask[g] = invalid ? 1 : 0;
-                if (p.ratio) p.ratio[g] = ratio;
-            }
-            __syncwarp();
         }
     }
+    if (queued) soa_flush_tail<W>(p, queue, queued, lane);
 
     tmem_fence_before();
     __syncthreads();
