@@ -19,10 +19,12 @@
 //   E   epilogue: min / first-max / flat neighbours / second peak / FP32 ratio fit on the fft-shifted map
 //
 // Versus piv_fused_kernel: all FFT arithmetic is packed FADD2 / FMUL2 / FFMA2 with immediate twiddles (the
-// radix-2 steps across a pair are the only scalar FP32 work), 13-22 % fewer executed instructions, 76-104 bytes
-// of spills instead of 472 at 64 px, 20 instead of 16 resident warps at 32 px.  What bounds both generations is
-// instruction supply: the per-job code (46 KB at 32 px CWS, 72 KB at 64 px) is larger than what an SM streams at
-// full rate (~44 KB, tests/micro/icache_stream.cu); DESIGN.md section 3.1 has the measurements and the list of
+// radix-2 steps across a pair are the only scalar FP32 work), 13-22 % fewer executed instructions, 20 instead of 16
+// resident warps at 32 px.  The map-dependent part of the epilogue runs per job; its scalar tail (sub-pixel fit,
+// ratio test, predictor replacement, stores) is batched: soa_flush_tail handles 16 queued windows, one per lane.
+// What bounds the kernel is latency per warp-instruction at 3-5 resident warps per scheduler (register file and
+// shared memory are both full); the instruction cache (per-job code 46-72 KB against 32 KB of L1.5) costs ~7 %
+// (stub builds, profiles/r02g_stub_ipc.txt).  DESIGN.md section 3.1 has the measurements and the list of
 // restructurings that were tried.
 #pragma once
 #include "piv_fused.cuh"
