@@ -49,7 +49,7 @@ def test_windows_any_size_bit_exact(G, w, o):
     assert np.array_equal(wb, O.interpolation_dws(b, idx, ix[:, None, None], iy[:, None, None]).astype(np.float32))
 
 
-@pytest.mark.parametrize("w", [48, 24, 128, 20, 6, 42, 28, 66, 104, 100, 160, 34, 4])   # 34 = 2 x 17: direct sums
+@pytest.mark.parametrize("w", [48, 24, 128, 20, 6, 42, 28, 66, 104, 100, 160, 34, 4, 192, 200, 256])   # 34 = 2 x 17: direct sums; > 160: global scratch
 def test_correlate_any_size(T, w):
     rng = np.random.default_rng(w)
     a = rng.integers(0, 256, (5, w, w), dtype=np.uint8)

@@ -478,7 +478,7 @@ def test_error_codes_through_c_abi(G):
     assert L.pivb200_pass_first(*args(48, 48)) == _lib.E_OVERLAP
     assert L.pivb200_pass_first(*args(128, 0)) == _lib.E_FRAME
     assert L.pivb200_pass_first(*args(130, 0)) == _lib.E_FRAME       # a valid size for the general kernel, but > 64 px
-    assert L.pivb200_pass_first(*args(162, 0)) == _lib.E_WINDOW
+    assert L.pivb200_pass_first(*args(258, 0)) == _lib.E_WINDOW
     assert L.pivb200_pass_first(*args(64, 0)) == 0
     bad = list(args(32, 16)); bad[11] = None
     assert L.pivb200_pass_first(*bad) == _lib.E_ARG

@@ -17,7 +17,7 @@ def timeit(fn, n=3):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 out = []
-for (w, o, mp, mode, sc, name) in [(48, 24, 1, "CWS", 2.0, "w48"), (128, 64, 1, "CWS", 2.0, "w128"), (160, 80, 1, "CWS", 2.0, "w160"),
+for (w, o, mp, mode, sc, name) in [(48, 24, 1, "CWS", 2.0, "w48"), (128, 64, 1, "CWS", 2.0, "w128"), (160, 80, 1, "CWS", 2.0, "w160"), (256, 128, 1, "CWS", 2.0, "w256"), (200, 100, 2, "CWS", 2.0, "cws200+100"),
                                    (24, 12, 1, "CWS", 2.0, "w24"), (48, 24, 2, "CWS", 2.0, "cws48+24"),
                                    (64, 32, 2, "CWS", 1.5, "cws64+42"), (128, 64, 3, "CWS", 2.0, "cws128+64+32"),
                                    (68, 34, 1, "CWS", 2.0, "w68(direct)")]:

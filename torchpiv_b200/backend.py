@@ -11,7 +11,7 @@ NikNazarov/TorchPIV ("PB"), so scripts written against the reference run unchang
 All numerical work goes through the C ABI of ``libpivb200.so`` (hand-written sm_100a kernels).
 There is no CPU path: ``device="cpu"`` raises, and a missing library raises on first use.
 Differences from the reference, all documented in DESIGN.md: interrogation windows must be even
-and at most 160 px (16/32/64 px take the fused kernels, other sizes a general mixed-radix kernel); the
+and at most 256 px (16/32/64 px take the fused kernels, other sizes a general mixed-radix kernel); the
 first pass is evaluated in FP32 (the reference uses FP64) -- results agree within 1e-3 px; exact
 ties between correlation values may resolve differently.
 """

@@ -1,4 +1,4 @@
-// General-size pass: interrogation windows of ANY even size up to 128 px (the reference accepts any
+// General-size pass: interrogation windows of ANY even size up to 256 px (the reference accepts any
 // window, e.g. 48 px or the 42 / 28 px that multipass_scale = 1.5 produces; PB:453-456, 855-857).
 //
 // The fused in-register FFT kernels (piv_fused.cuh) exist for 16 / 32 / 64 px only.  Everything else
@@ -35,7 +35,9 @@ __host__ __device__ constexpr double generic_ct_cos(double x) {
 }
 __host__ __device__ constexpr double generic_ct_sin(double x) { return generic_ct_cos(x - 0.25); }
 
-constexpr int kGenericMaxWindow = 160;           // bounded by shared memory: w (w + 1) complex values
+constexpr int kGenericMaxWindow = 256;           // the reference's GUI limit (ControlsWidgets.py:91)
+constexpr int kGenericMaxSharedWindow = 160;     // up to here the w (w + 1) complex values of a window fit shared memory;
+                                                 // larger windows keep them in a global scratch slab (L2-resident)
 constexpr int kGenericThreads = 512;             // upper bound; generic_threads(w) picks the block size
 constexpr int kGenericMaxStages = 8;
 constexpr int kGenericShiftClamp = 1 << 20;          // same documented clamp as the fused kernels
@@ -60,6 +62,7 @@ struct GenericParams {
     float* corr_out;                       // [n_windows][w][w], fft-shifted
     float* win_a_out;                      // optional: the (shifted) windows themselves
     float* win_b_out;
+    float2* zglobal;                       // windows above kGenericMaxSharedWindow: one w (w + 1) slab per CTA, else null
     int n_stages;                          // mixed-radix plan of the window size (0 = direct sums); generic_set_plan
     int radix[kGenericMaxStages];
     int blk[kGenericMaxStages];            // block size M of stage s (decimation in frequency order): w, w / R0, ...
@@ -367,12 +370,13 @@ __device__ __forceinline__ void generic_lines(float2* Z, const float2* tw, int w
     else generic_lines_r<1>(Z, tw, w, pitch, columns, conj);
 }
 
-template <bool BIG>
+// GZ: the window's complex array lives in global memory (p.zglobal) instead of shared memory
+template <bool BIG, bool GZ = false>
 __global__ void __launch_bounds__(BIG ? kGenericThreads : 256, BIG ? 1 : 4) generic_corr_kernel(const GenericParams p) {
     extern __shared__ __align__(16) unsigned char gsm[];
     const int w = p.wind, pitch = w + 1, half = w / 2;
-    float2* Z = reinterpret_cast<float2*>(gsm);
-    float2* tw = Z + w * pitch;
+    float2* Z = GZ ? p.zglobal + static_cast<size_t>(blockIdx.x) * w * pitch : reinterpret_cast<float2*>(gsm);
+    float2* tw = GZ ? reinterpret_cast<float2*>(gsm) : Z + w * pitch;
     float* red = reinterpret_cast<float*>(tw + w);
     unsigned short* pos_of = reinterpret_cast<unsigned short*>(red + 64);     // bin k -> position (digit reversal)
     unsigned short* bin_at = pos_of + w;                                      // position -> bin
@@ -547,8 +551,8 @@ __global__ void generic_glue_kernel(const double* __restrict__ du, const double*
 inline bool generic_window_ok(int wind) { return wind >= 4 && wind <= kGenericMaxWindow && wind % 2 == 0; }
 
 inline size_t generic_smem_bytes(int w) {
-    return static_cast<size_t>(w) * (w + 1) * sizeof(float2) + static_cast<size_t>(w) * sizeof(float2) + 64 * sizeof(float) +
-           2 * static_cast<size_t>(w) * sizeof(unsigned short);
+    const size_t z = (w <= kGenericMaxSharedWindow) ? static_cast<size_t>(w) * (w + 1) * sizeof(float2) : 0;
+    return z + static_cast<size_t>(w) * sizeof(float2) + 64 * sizeof(float) + 2 * static_cast<size_t>(w) * sizeof(unsigned short);
 }
 
 // threads per window: small windows are latency-bound by their ~25 block-wide phases, so they get small blocks
@@ -583,7 +587,8 @@ inline int generic_launch(const GenericParams& gp_in, cudaStream_t s) {
     const int threads = generic_threads(gp.wind);
     bool big = threads > 256;
     for (int i = 0; i < gp.n_stages; ++i) big = big || gp.radix[i] > 8;
-    auto kern = big ? generic_corr_kernel<true> : generic_corr_kernel<false>;
+    const bool gz = gp.wind > kGenericMaxSharedWindow;
+    auto kern = gz ? generic_corr_kernel<true, true> : (big ? generic_corr_kernel<true> : generic_corr_kernel<false>);
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (err != cudaSuccess) return static_cast<int>(err);
     int dev = 0, sms = 0, per_sm = 1;
@@ -592,9 +597,17 @@ inline int generic_launch(const GenericParams& gp_in, cudaStream_t s) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
     long long grid = static_cast<long long>(sms) * (per_sm > 0 ? per_sm : 1);
     if (grid > gp.n_windows) grid = gp.n_windows;
+    gp.zglobal = nullptr;
+    if (gz) {           // stream-ordered scratch: grid slabs of w (w + 1) complex values (78 MB for 256 px on 148 SMs)
+        err = cudaMallocAsync(reinterpret_cast<void**>(&gp.zglobal),
+                              static_cast<size_t>(grid) * gp.wind * (gp.wind + 1) * sizeof(float2), s);
+        if (err != cudaSuccess) return static_cast<int>(err);
+    }
     kern<<<static_cast<unsigned>(grid), threads, smem, s>>>(gp);
     count_launch();
-    return static_cast<int>(cudaGetLastError());
+    err = cudaGetLastError();
+    if (gz) cudaFreeAsync(gp.zglobal, s);
+    return static_cast<int>(err);
 }
 
 // A whole pass for a general window size: correlation maps in chunks through a stream-ordered scratch

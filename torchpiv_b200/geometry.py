@@ -16,7 +16,7 @@ import numpy as np
 __all__ = ["get_field_shape", "get_coordinates", "spline_operator"]
 
 FUSED_WINDOWS = (16, 32, 64)          # fused in-register FFT kernels
-MAX_WINDOW = 160                      # general-size path (mixed-radix FFT in shared memory): any even size up to this
+MAX_WINDOW = 256                      # general-size path (mixed-radix FFT in shared memory): any even size up to this
 SUPPORTED_WINDOWS = FUSED_WINDOWS     # kept for callers that ask which sizes take the fast path
 
 
