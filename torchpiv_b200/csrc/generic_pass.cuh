@@ -20,6 +20,7 @@
 // Included by pivb200.cu (needs corr_to_disp_kernel and grid_for).
 #pragma once
 #include "fft_regs.cuh"
+#include "fft_soa.cuh"
 
 namespace pivb200 {
 
@@ -213,8 +214,9 @@ __device__ __forceinline__ void generic_lines_r(float2* Z, const float2* tw, int
 // R-point DFT, forward sign (e^{-2 pi i t q / R}), natural order in and out
 template <int R>
 __device__ __forceinline__ void generic_small_dft(float2 (&v)[R]) {
-    auto add = [](float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); };
-    auto sub = [](float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); };
+    // complex additions are packed FADD2 (one instruction for re and im)
+    auto add = [](float2 a, float2 b) { return padd(a, b); };
+    auto sub = [](float2 a, float2 b) { return psub(a, b); };
     auto mul_mi = [](float2 a) { return make_float2(a.y, -a.x); };                  // * -i
     if constexpr (R == 2) {
         const float2 t = sub(v[0], v[1]);
@@ -426,24 +428,52 @@ __global__ void __launch_bounds__(BIG ? kGenericThreads : 256, BIG ? 1 : 4) gene
             }
             // a lane keeps its column(s): the x-axis taps are computed once per column, the y-axis taps once per pixel row;
             // frame a is shifted by -s, frame b by +s (PB:720-723 / 792-795)
-            for (int j = tx; j < w; j += 32) {
-                GenericAxis xa, xb;
-                if (cws) { xa = generic_axis(c0 + j, -vxf); xb = generic_axis(c0 + j, vxf); }
-                for (int i = ty; i < w; i += nwy) {
-                    float a, b;
-                    if (cws) {
-                        a = generic_bilinear(p, fa, generic_axis(r0 + i, -vyf), xa);
-                        b = generic_bilinear(p, fb, generic_axis(r0 + i, vyf), xb);
-                    } else {
-                        a = generic_at(p, fa, r0 + i - vyi, c0 + j - vxi);
-                        b = generic_at(p, fb, r0 + i + vyi, c0 + j + vxi);
+            auto put = [&](int i, int j, float a, float b) {
+                Z[i * pitch + j] = make_float2(a, b);
+                sum_a += a;
+                sum_b += b;
+                if (p.win_a_out) {
+                    p.win_a_out[g * w * w + i * w + j] = a;
+                    p.win_b_out[g * w * w + i * w + j] = b;
+                }
+            };
+            // unshifted / integer-shifted windows that lie inside the frame (the common case): plain byte loads, four rows
+            // in flight per lane
+            const bool inside = !cws && r0 - abs(vyi) >= 0 && r0 + w + abs(vyi) <= p.H && c0 - abs(vxi) >= 0 &&
+                                c0 + w + abs(vxi) <= p.Wf;
+            if (inside) {
+                const unsigned char* pa = fa + static_cast<long long>(r0 - vyi) * p.pitch + (c0 - vxi);
+                const unsigned char* pb = fb + static_cast<long long>(r0 + vyi) * p.pitch + (c0 + vxi);
+                for (int j = tx; j < w; j += 32) {
+                    int i = ty;
+                    for (; i + 3 * nwy < w; i += 4 * nwy) {
+                        unsigned char va[4], vb[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            va[t] = pa[static_cast<long long>(i + t * nwy) * p.pitch + j];
+                            vb[t] = pb[static_cast<long long>(i + t * nwy) * p.pitch + j];
+                        }
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) put(i + t * nwy, j, static_cast<float>(va[t]), static_cast<float>(vb[t]));
                     }
-                    Z[i * pitch + j] = make_float2(a, b);
-                    sum_a += a;
-                    sum_b += b;
-                    if (p.win_a_out) {
-                        p.win_a_out[g * w * w + i * w + j] = a;
-                        p.win_b_out[g * w * w + i * w + j] = b;
+                    for (; i < w; i += nwy)
+                        put(i, j, static_cast<float>(pa[static_cast<long long>(i) * p.pitch + j]),
+                            static_cast<float>(pb[static_cast<long long>(i) * p.pitch + j]));
+                }
+            } else {
+                for (int j = tx; j < w; j += 32) {
+                    GenericAxis xa, xb;
+                    if (cws) { xa = generic_axis(c0 + j, -vxf); xb = generic_axis(c0 + j, vxf); }
+                    for (int i = ty; i < w; i += nwy) {
+                        float a, b;
+                        if (cws) {
+                            a = generic_bilinear(p, fa, generic_axis(r0 + i, -vyf), xa);
+                            b = generic_bilinear(p, fb, generic_axis(r0 + i, vyf), xb);
+                        } else {
+                            a = generic_at(p, fa, r0 + i - vyi, c0 + j - vxi);
+                            b = generic_at(p, fb, r0 + i + vyi, c0 + j + vxi);
+                        }
+                        put(i, j, a, b);
                     }
                 }
             }
