@@ -15,9 +15,10 @@
  *   - masks: 1 = INVALID vector (the reference's `validation_mask` True);
  *   - window index n = row * n_cols + col (row-major), pair index outermost: g = pair * n + n;
  *   - interrogation windows of 16, 32 or 64 px run the fused in-register FFT kernels; any other
- *     EVEN size from 4 to 256 px runs a general kernel (in-place mixed-radix FFT in shared memory,
- *     radices 2-16, direct sums for sizes with a prime factor above 13, the window in shared memory up to 160 px and in an L2-resident scratch slab above; same semantics; scratch memory
- *     comes from cudaMallocAsync on `stream`);
+ *     EVEN size from 4 to 256 px runs a general kernel (in-place mixed-radix FFT, radices 2-16,
+ *     direct sums for sizes with a prime factor above 13; the window lives in shared memory up to
+ *     160 px and in an L2-resident scratch slab above; same semantics; scratch memory comes from
+ *     cudaMallocAsync on `stream`);
  *     odd sizes and sizes above 256 px return PIVB200_E_WINDOW.  There is no CPU fallback
  *     anywhere in this library.
  */

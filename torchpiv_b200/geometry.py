@@ -21,7 +21,7 @@ SUPPORTED_WINDOWS = FUSED_WINDOWS     # kept for callers that ask which sizes ta
 
 
 def window_supported(wind: int) -> bool:
-    """Sizes the library can process: even, 4..128 px (16/32/64 px take the fused kernels)."""
+    """Sizes the library can process: even, 4..256 px (16/32/64 px take the fused kernels)."""
     return int(wind) == wind and 4 <= wind <= MAX_WINDOW and wind % 2 == 0
 
 
