@@ -7,7 +7,7 @@ from torchpiv_b200 import synth
 shape = (2048, 2048)
 noise, blank = synth.default_patches(shape)
 a, b = synth.particle_pair(shape, synth.uniform_shift(3.3, -2.2), seed=0, noise_patch=noise, blank_patch=blank)
-B = 16
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 fa = torch.from_numpy(a).cuda()[None].expand(B, -1, -1).contiguous()
 fb = torch.from_numpy(b).cuda()[None].expand(B, -1, -1).contiguous()
 def timeit(fn, n=8):
