@@ -507,6 +507,10 @@ def run_ours(args):
                                        w1["pred_v"].data_ptr(), 1, 1.2, w1["u"].data_ptr(), w1["v"].data_ptr(),
                                        w1["mask"].data_ptr(), None, st))
 
+    # the legs above ran the same plan on other inputs (the sequential-folder leg pairs unrelated frames): restore the
+    # benchmark's own predictor field in the workspace, so that the second pass is timed on the shifts of the timed region
+    plan.run(fa, fb)
+    torch.cuda.synchronize(dev)
     ms_first, ms_next = time_kernel(k_first), time_kernel(k_next)
     peak = ctypes.c_double()
     _lib.check(L.pivb200_measure_fp32_peak(10, ctypes.byref(peak), st))
