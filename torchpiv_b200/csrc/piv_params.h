@@ -66,7 +66,7 @@ struct PassParams {
     unsigned char* mask;             // 1 = invalid (peak ratio test), may be null when !validate
     float* ratio;                    // optional peak / second-peak ratio
     int use_tma;
-    int sync_mask;                   // bit s: barrier before FFT step s (0..5)
+    int sync_mask;                   // bit s: barrier at phase boundary s (piv_soa.cuh: 0..6)
     int sync_group;                  // 1: barriers span groups of four warps instead of the CTA
     int skew_ns;                     // initial delay of group g: g * skew_ns
     // explicit loaders / debug sinks

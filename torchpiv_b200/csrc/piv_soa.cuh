@@ -316,7 +316,8 @@ __global__ void __launch_bounds__(SmemS<W, LOADER>::NWARPS * 32, 1) piv_soa_kern
     auto stage_issue = [&](int frame) { stage_tiles<W, LOADER>(&tmA, &tmB, p, smem, frame, lane); };
 
     // optional lock step (instruction-fetch sharing): bit i of p.sync_mask puts a named barrier over groups of
-    // p.sync_group warps at phase boundary i (0 rows, 1 columns, 2 product, 3 inverse columns, 4 inverse rows, 5 epilogue)
+    // p.sync_group warps at phase boundary i (0 rows of frame a, 1 columns, 2 product, 3 inverse columns, 4 inverse rows,
+    // 5 epilogue, 6 rows of frame b)
     auto lockstep = [&](int point) {
         if ((p.sync_mask >> point) & 1) {
             // sync_group == 0: the warps of one scheduler (warp & 3) form a group -- they share the scheduler's L0
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(SmemS<W, LOADER>::NWARPS * 32, 1) piv_soa_kern
 #pragma unroll 1
         for (int frame = 0; frame < 2; ++frame) {
             // ------------------------------------------------------------- tiles -> rows (2l, 2l+1) in x[j]
-            lockstep(0);
+            lockstep(frame == 0 ? 0 : 6);
             mbar_wait(bar, static_cast<uint32_t>(frame));
             const TileDesc* desc = reinterpret_cast<const TileDesc*>(smem + S::TD_OFF);
             if constexpr (LOADER == LD_FRAME_INT || LOADER == LD_FRAME_CWS) {

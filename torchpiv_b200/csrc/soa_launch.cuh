@@ -28,14 +28,14 @@ static int launch_soa_one(const CUtensorMap& ta, const CUtensorMap& tb, const Pa
     // lock-step barriers (piv_soa.cuh): PIVB200_SOA_SYNC = mask of phase boundaries, PIVB200_SOA_GROUP = warps per group
     // (0 = the warps of one scheduler).  Measured best on B200 (profiles/r02h_lockstep_sweep.txt): ONE meeting point per job.
     // The 64 px kernels (72 KB of per-job code, 3 warps per scheduler; meeting before the product) and the 32 px CWS
-    // kernel (meeting before the inverse row transform) want the warps of a SCHEDULER in step -- they share its
+    // kernel (meeting before frame b's row transform: bit 6) want the warps of a SCHEDULER in step -- they share its
     // instruction fetches: 8 % for the 64 px pass, 4 % for the CWS pass --, the other kernels groups of four consecutive
     // warps (one per scheduler) meeting before the product, whose FP32-bound and shared-memory-bound phases overlap
     // inside a scheduler.  Meeting at every boundary, or CTA-wide, is slower everywhere.
     static const int env_sync = [] { const char* e = getenv("PIVB200_SOA_SYNC"); return e ? atoi(e) : -1; }();
     static const int env_group = [] { const char* e = getenv("PIVB200_SOA_GROUP"); return e ? atoi(e) : -1; }();
     constexpr bool per_scheduler = (W == 64) || (W == 32 && LOADER == LD_FRAME_CWS);
-    p.sync_mask = env_sync >= 0 ? env_sync : ((W == 32 && LOADER == LD_FRAME_CWS) ? 16 : 4);
+    p.sync_mask = env_sync >= 0 ? env_sync : ((W == 32 && LOADER == LD_FRAME_CWS) ? 64 : 4);
     p.sync_group = env_group >= 0 ? env_group : (per_scheduler ? 0 : 4);
     using S = SmemS<W, LOADER>;
     auto kern = piv_soa_kernel<W, LOADER>;
