@@ -23,9 +23,10 @@
 // resident warps at 32 px.  The map-dependent part of the epilogue runs per job; its scalar tail (sub-pixel fit,
 // ratio test, predictor replacement, stores) is batched: soa_flush_tail handles 16 queued windows, one per lane.
 // What bounds the kernel is latency per warp-instruction at 3-5 resident warps per scheduler (register file and
-// shared memory are both full); the instruction cache (per-job code 46-72 KB against 32 KB of L1.5) costs ~7 %
-// (stub builds, profiles/r02g_stub_ipc.txt).  DESIGN.md section 3.1 has the measurements and the list of
-// restructurings that were tried.
+// shared memory are both full) on top of an FP32 pipe that the transform phases saturate with one or two warps.
+// Instruction supply (per-job code 46-72 KB against 32 KB of L1.5) is the second-order term: the warps of one
+// scheduler run in lock step from one meeting point per job (soa_launch.cuh) and share their fetches, worth 8 % at
+// 64 px.  DESIGN.md section 3.1 has the measurements and the list of restructurings that were tried.
 #pragma once
 #include "piv_fused.cuh"
 #include "piv_soa_math.cuh"
