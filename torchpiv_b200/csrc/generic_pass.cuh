@@ -9,13 +9,17 @@
 // correlation_to_displacement (corr_to_disp_kernel, PB:346-422) and the predictor glue (PB:728-738 /
 // 800-810) follow as two small kernels.
 //
-// The transform is a mixed-radix FFT (radices 8, 4, 2, 3, 5, 7, 11, 13) done IN PLACE without any reordering
+// The transform is a mixed-radix FFT (radices 16, 8, 4, 2, 3, 5, 7, 11, 13) done IN PLACE without any reordering
 // pass: decimation in frequency forward (natural order in, digit-reversed order out), the spectrum product
 // P = conj(A^) B^ in the digit-reversed index space (partner bin -k through a small position table), and a
-// decimation-in-time transform back (digit-reversed in, natural out).  Work items are (line, butterfly)
-// pairs with the LINE index fastest across the lanes: every shared-memory access of a pass is then either
-// contiguous or strided by the odd row pitch, i.e. bank-conflict free for any window size.  Sizes with a
-// prime factor above 13 (22 = 2 x 11 is fine, 34 = 2 x 17 is not) fall back to direct sums (O(w^3 / r)).
+// decimation-in-time transform back (digit-reversed in, natural out).  A warp takes one butterfly index, its
+// lanes take the lines: every shared-memory access of a pass is then either contiguous or strided by the odd
+// row pitch, i.e. bank-conflict free for any window size.  Sizes with a prime factor above 13 (22 = 2 x 11 is
+// fine, 34 = 2 x 17 is not) fall back to direct sums (O(w^3 / r)).  Windows of 162-256 px keep their complex
+// array in a global scratch slab (one per CTA, L2-resident) instead of shared memory; same code otherwise.
+// Three instantiations: <false> (radices up to 8, 64 registers, up to 256 threads: small windows are bound by
+// the latency of their ~25 block-wide phases and want many resident blocks), <true> (all radices, 512 threads),
+// <true, true> (global slab).
 //
 // Included by pivb200.cu (needs corr_to_disp_kernel and grid_for).
 #pragma once
