@@ -15,12 +15,13 @@
  *   - masks: 1 = INVALID vector (the reference's `validation_mask` True);
  *   - window index n = row * n_cols + col (row-major), pair index outermost: g = pair * n + n;
  *   - interrogation windows of 16, 32 or 64 px run the fused in-register FFT kernels; any other
- *     EVEN size from 4 to 256 px runs a general kernel (in-place mixed-radix FFT, radices 2-16,
+ *     size from 4 to 256 px runs a general kernel (in-place mixed-radix FFT, radices 2-16,
  *     direct sums for sizes with a prime factor above 13; the window lives in shared memory up to
  *     160 px and in an L2-resident scratch slab above; same semantics; scratch memory comes from
- *     cudaMallocAsync on `stream`);
- *     odd sizes and sizes above 256 px return PIVB200_E_WINDOW.  There is no CPU fallback
- *     anywhere in this library.
+ *     cudaMallocAsync on `stream`).  ODD sizes reproduce the reference's behaviour: torch.fft.irfft2
+ *     without an explicit size returns a [w, w-1] correlation map for them (PB:255), and so do
+ *     pivb200_correlate and the passes internally.  Sizes below 4 or above 256 px return
+ *     PIVB200_E_WINDOW.  There is no CPU fallback anywhere in this library.
  */
 #ifndef PIVB200_H_
 #define PIVB200_H_
@@ -32,7 +33,7 @@ extern "C" {
 #endif
 
 #define PIVB200_OK 0
-#define PIVB200_E_WINDOW (-1)   /* window size odd, < 4 or > 256                         */
+#define PIVB200_E_WINDOW (-1)   /* window size < 4 or > 256                              */
 #define PIVB200_E_OVERLAP (-2)  /* overlap >= window (PB:503-504 raises ValueError)      */
 #define PIVB200_E_FRAME (-3)    /* window larger than the frame (PB:506-507), bad pitch  */
 #define PIVB200_E_ARG (-4)      /* null / misaligned pointer, non-positive count         */

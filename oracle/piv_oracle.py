@@ -141,7 +141,9 @@ def correlate_fft(images_a: np.ndarray, images_b: np.ndarray, workers: int = -1)
     fb = _sfft.rfft2(images_b, workers=workers)
     np.conjugate(fa, out=fa)
     fa *= fb
-    corr = _sfft.irfft2(fa, s=images_a.shape[-2:], workers=workers)
+    # no `s=`: like torch.fft.irfft2 in the reference, the last axis comes back with 2 (m - 1) samples -- w for an
+    # even window, w - 1 for an odd one (the reference's map for odd windows is [w, w - 1]; PB:255)
+    corr = _sfft.irfft2(fa, workers=workers)
     return _sfft.fftshift(corr, axes=(-2, -1))
 
 

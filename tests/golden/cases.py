@@ -17,7 +17,8 @@ from torchpiv_b200 import synth  # noqa: E402
 GOLDEN_DIR = os.path.dirname(os.path.abspath(__file__))
 SMALL_SHAPE = (288, 352)
 PASS1_GEOMS = [(64, 32), (32, 16), (16, 8), (32, 8), (64, 48)]
-GENERAL_GEOMS = [(48, 24), (24, 12), (128, 64), (20, 6), (42, 21), (96, 48), (160, 80), (192, 64), (256, 200)]   # not 16/32/64: general kernel
+GENERAL_GEOMS = [(48, 24), (24, 12), (128, 64), (20, 6), (42, 21), (96, 48), (160, 80), (192, 64), (256, 200),
+                 (25, 12), (35, 17), (31, 15), (63, 31)]   # not 16/32/64: general kernel; odd sizes: [w, w-1] maps
 
 
 def sha(*arrays) -> str:

@@ -236,6 +236,14 @@ def gen_general_sizes():
             u, v, x, y, m = quiet(fn, ta, tb, x, y, u.copy(), v.copy(), m.copy())
             out[f"{mode}_p{it}_u"], out[f"{mode}_p{it}_v"], out[f"{mode}_p{it}_mask"] = u, v, m
             out[f"{mode}_p{it}_x"], out[f"{mode}_p{it}_y"] = x, y
+    # halving into an ODD window: 50 -> 25 px (the reference's maps are then [25, 24], PB:255)
+    for mode in ("CWS", "DWS"):
+        u, v, x, y, m = PB.extended_search_area_piv(ta, tb, window_size=50, overlap=25, validate=True)
+        out[f"odd{mode}_p0_u"], out[f"odd{mode}_p0_v"], out[f"odd{mode}_p0_mask"] = u, v, m
+        fn = PB.IterModMap.functions[mode](ta.shape, 25, 12, CPU)
+        u, v, x, y, m = quiet(fn, ta, tb, x, y, u.copy(), v.copy(), m.copy())
+        out[f"odd{mode}_p1_u"], out[f"odd{mode}_p1_v"], out[f"odd{mode}_p1_mask"] = u, v, m
+        out[f"odd{mode}_p1_x"], out[f"odd{mode}_p1_y"] = x, y
     tmp = tempfile.mkdtemp(prefix="pivgold_")
     try:
         pairs = [cases.small_pair(seed=10 + i, kind="uniform" if i % 2 == 0 else "vortex") for i in range(2)]

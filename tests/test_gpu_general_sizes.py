@@ -49,7 +49,7 @@ def test_windows_any_size_bit_exact(G, w, o):
     assert np.array_equal(wb, O.interpolation_dws(b, idx, ix[:, None, None], iy[:, None, None]).astype(np.float32))
 
 
-@pytest.mark.parametrize("w", [48, 24, 128, 20, 6, 42, 28, 66, 104, 100, 160, 34, 4, 192, 200, 256])   # 34 = 2 x 17: direct sums; > 160: global scratch
+@pytest.mark.parametrize("w", [48, 24, 128, 20, 6, 42, 28, 66, 104, 100, 160, 34, 4, 192, 200, 256, 25, 35, 31, 9, 5, 63, 165, 131, 37])   # 34 = 2 x 17 and 31: direct sums; > 160: global scratch; odd: [w, w-1]
 def test_correlate_any_size(T, w):
     rng = np.random.default_rng(w)
     a = rng.integers(0, 256, (5, w, w), dtype=np.uint8)
@@ -57,9 +57,14 @@ def test_correlate_any_size(T, w):
     ref = O.correlate_fft(a.astype(np.float64), b.astype(np.float64))
     for arr_a, arr_b in ((a, b), (a.astype(np.float32), b.astype(np.float32))):
         got = T.correalte_fft(torch.from_numpy(arr_a).cuda(), torch.from_numpy(arr_b).cuda())
-        assert got.dtype == torch.float32 and tuple(got.shape) == (5, w, w)
+        assert got.dtype == torch.float32 and tuple(got.shape) == ref.shape
         got = got.cpu().numpy().astype(np.float64)
-        assert np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+        # sizes with a prime factor above 13 take FP32 direct sums (O(w) terms per bin instead of O(log w) stages)
+        n, big = w, 1
+        for q in range(2, w + 1):
+            while n % q == 0:
+                n, big = n // q, q
+        assert np.abs(got - ref).max() <= (5e-6 if big > 13 else 2e-6) * np.abs(ref).max()
         assert np.array_equal(got.reshape(5, -1).argmax(1), ref.reshape(5, -1).argmax(1))
 
 
@@ -73,7 +78,10 @@ def test_pass_first_any_size_vs_reference(T, golden, w, o):
     assert np.array_equal(x, g[f"p1_{w}_{o}_x"]) and np.array_equal(y, g[f"p1_{w}_{o}_y"])
     stash = {}
     O.extended_search_area_piv(a, b, w, o, validate=True, stash=stash)
-    check_field(u, v, m, g[f"p1_{w}_{o}_u"], g[f"p1_{w}_{o}_v"], g[f"p1_{w}_{o}_mask"], stash["corr"])
+    # odd windows: the reference's [w, w-1] maps are a warped correlation with flatter peaks -- a few more vectors are
+    # ill-conditioned by the oracle-side rule (35 px: 4 of the 226 valid ones)
+    check_field(u, v, m, g[f"p1_{w}_{o}_u"], g[f"p1_{w}_{o}_v"], g[f"p1_{w}_{o}_mask"], stash["corr"],
+                max_ill_valid=0.05 if w % 2 else 0.01)
 
 
 @pytest.mark.parametrize("mode", ["CWS", "DWS"])
@@ -96,6 +104,24 @@ def test_scale_1p5_chain_at_the_function_boundary(T, golden, mode):
         check_field(u, v, m, g[f"{mode}_p{it}_u"], g[f"{mode}_p{it}_v"], g[f"{mode}_p{it}_mask"], orc.last_corr,
                     max_ill=0.2)
         x, y = x1, y1
+
+
+@pytest.mark.parametrize("mode", ["CWS", "DWS"])
+def test_halving_into_an_odd_window(T, golden, mode):
+    """50 -> 25 px: the second pass runs on ODD windows ([25, 24] correlation maps like the reference's), fed with the
+    REFERENCE's first-pass field."""
+    g = golden("general_sizes.npz")
+    a, b = cases.small_pair(seed=3, kind="vortex", zero_patch=True)
+    fa, fb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    x, y = O.get_coordinates(a.shape, 50, 25)
+    prev = [g[f"odd{mode}_p0_{k}"] for k in ("u", "v", "mask")]
+    fn = T.IterModMap.functions[mode](a.shape, 25, 12, "cuda:0")
+    u, v, x1, y1, m = fn(fa, fb, x, y, prev[0].copy(), prev[1].copy(), prev[2].copy())
+    assert np.array_equal(x1, g[f"odd{mode}_p1_x"]) and np.array_equal(y1, g[f"odd{mode}_p1_y"])
+    orc = O.ITER_MODES[mode](a.shape, 25, 12)
+    orc(a, b, x, y, prev[0].copy(), prev[1].copy(), prev[2].copy())
+    check_field(u, v, m, g[f"odd{mode}_p1_u"], g[f"odd{mode}_p1_v"], g[f"odd{mode}_p1_mask"], orc.last_corr, max_ill=0.2,
+                max_ill_valid=0.05)
 
 
 def test_offline_piv_with_scale_1p5(T, golden, tmp_path):

@@ -51,7 +51,7 @@ def test_error_strings_and_geometry_checks_without_gpu():
     assert "larger than the image" in _lib.error_string(_lib.E_FRAME)
     # argument validation happens before any CUDA call, so it is testable here
     dummy = ctypes.c_void_p(0x1000)
-    for bad_window in (47, 258, 2):      # odd / above 256 / below 4 (48 would take the general kernel)
+    for bad_window in (258, 3, 2):      # above 256 / below 4 (47 or 48 would take the general kernel)
         rc = L.pivb200_pass_first(dummy, dummy, 1, 0, 256, 256, 256, bad_window, 0, 1, 1.2, dummy, dummy, dummy,
                                   None, None)
         assert rc == _lib.E_WINDOW

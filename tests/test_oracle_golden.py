@@ -162,7 +162,10 @@ def test_pass1_general_window_sizes(golden, w, o):
     u, v, x, y, m = O.extended_search_area_piv(a, b, w, o, validate=True)
     assert np.array_equal(m, g[f"p1_{w}_{o}_mask"])
     assert np.array_equal(x, g[f"p1_{w}_{o}_x"]) and np.array_equal(y, g[f"p1_{w}_{o}_y"])
-    assert np.abs(u - g[f"p1_{w}_{o}_u"]).max() < TOL64 and np.abs(v - g[f"p1_{w}_{o}_v"]).max() < TOL64
+    # odd windows ([w, w-1] maps): pocketfft's odd-length transforms in SciPy and torch round differently, and a
+    # near-degenerate window amplifies that to 3e-7 px at one vector of the 35 px case
+    tol = 1e-6 if w % 2 else TOL64
+    assert np.abs(u - g[f"p1_{w}_{o}_u"]).max() < tol and np.abs(v - g[f"p1_{w}_{o}_v"]).max() < tol
 
 
 @pytest.mark.parametrize("mode", ["CWS", "DWS"])

@@ -10,8 +10,8 @@ NikNazarov/TorchPIV ("PB"), so scripts written against the reference run unchang
 
 All numerical work goes through the C ABI of ``libpivb200.so`` (hand-written sm_100a kernels).
 There is no CPU path: ``device="cpu"`` raises, and a missing library raises on first use.
-Differences from the reference, all documented in DESIGN.md: interrogation windows must be even
-and at most 256 px (16/32/64 px take the fused kernels, other sizes a general mixed-radix kernel); the
+Differences from the reference, all documented in DESIGN.md: interrogation windows are 4..256 px
+(16/32/64 px take the fused kernels, other sizes -- odd ones included -- a general mixed-radix kernel); the
 first pass is evaluated in FP32 (the reference uses FP64) -- results agree within 1e-3 px; exact
 ties between correlation values may resolve differently.
 """
@@ -123,7 +123,8 @@ def moving_window_array(array: torch.Tensor, window_size, overlap) -> torch.Tens
 
 def correalte_fft(images_a: torch.Tensor, images_b: torch.Tensor) -> torch.Tensor:
     """fft-shifted circular cross-correlation of two window stacks ``[c, w, w]`` (PB:249-257),
-    ``corr[s] = sum_x a[x] b[x+s]`` with zero lag at ``(w/2, w/2)``.  uint8 and float32 inputs
+    ``corr[s] = sum_x a[x] b[x+s]`` with zero lag at ``(w/2, w/2)``; for odd ``w`` the map is ``[c, w, w-1]`` like
+    the reference's (``irfft2`` without an explicit size).  uint8 and float32 inputs
     give float32 like the reference; float64 inputs are evaluated in FP32 and returned as
     float64."""
     if images_a.shape != images_b.shape or images_a.dim() != 3 or images_a.shape[-1] != images_a.shape[-2]:
@@ -135,7 +136,8 @@ def correalte_fft(images_a: torch.Tensor, images_b: torch.Tensor) -> torch.Tenso
     else:
         code, a, b = 0, images_a.float().contiguous(), images_b.float().contiguous()
     c, w, _ = a.shape
-    corr = torch.empty((c, w, w), dtype=torch.float32, device=dev)
+    # odd windows: [c, w, w - 1], what torch.fft.irfft2 returns in the reference (PB:255)
+    corr = torch.empty((c, w, w - (w & 1)), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):      # the C ABI launches on the CURRENT device
         _lib.check(_lib.lib().pivb200_correlate(a.data_ptr(), b.data_ptr(), code, c, w, corr.data_ptr(),
                                                 _stream(dev)))

@@ -141,9 +141,8 @@ __device__ __forceinline__ float block_reduce(float v, float* red, int op) {   /
 __device__ __forceinline__ float2 gmul(float2 a, float2 t) {
     return make_float2(fmaf(a.x, t.x, -a.y * t.y), fmaf(a.x, t.y, a.y * t.x));
 }
-template <int R>
+template <int R, int J = 4 / R>                  // J = outputs k' per lane
 __device__ __forceinline__ void generic_lines_r(float2* Z, const float2* tw, int w, int pitch, bool columns, bool conj) {
-    constexpr int J = 4 / R;                     // outputs k' per lane
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int es = columns ? pitch : 1, ls = columns ? 1 : pitch;
     const int m = w / R;
@@ -372,18 +371,24 @@ __device__ __forceinline__ int generic_pos(const GenericParams& p, int k, int w)
 
 __device__ __forceinline__ void generic_lines(float2* Z, const float2* tw, int w, int pitch, bool columns, bool conj) {
     if (w % 4 == 0 && w >= 96) generic_lines_r<4>(Z, tw, w, pitch, columns, conj);
-    else if (w >= 16) generic_lines_r<2>(Z, tw, w, pitch, columns, conj);
-    else generic_lines_r<1>(Z, tw, w, pitch, columns, conj);
+    else if (w % 2 == 0 && w >= 16) generic_lines_r<2>(Z, tw, w, pitch, columns, conj);
+    else if (w <= 128) generic_lines_r<1>(Z, tw, w, pitch, columns, conj);
+    else generic_lines_r<1, 8>(Z, tw, w, pitch, columns, conj);          // odd sizes above 128 px
 }
 
 // GZ: the window's complex array lives in global memory (p.zglobal) instead of shared memory
 template <bool BIG, bool GZ = false>
 __global__ void __launch_bounds__(BIG ? kGenericThreads : 256, BIG ? 1 : 4) generic_corr_kernel(const GenericParams p) {
     extern __shared__ __align__(16) unsigned char gsm[];
-    const int w = p.wind, pitch = w + 1, half = w / 2;
+    // odd windows: the reference's irfft2 returns a [w, w - 1] map (PB:255; torch.fft.irfft2 without `s`): the inverse
+    // transform along x is a length-(w - 1) c2r over the bins 0 .. (w - 1) / 2 of the length-w spectrum
+    const int w = p.wind, pitch = w | 1, half = w / 2;
+    const bool odd = (w & 1) != 0;
+    const int nx = odd ? w - 1 : w;                                       // columns of the map
     float2* Z = GZ ? p.zglobal + static_cast<size_t>(blockIdx.x) * w * pitch : reinterpret_cast<float2*>(gsm);
     float2* tw = GZ ? reinterpret_cast<float2*>(gsm) : Z + w * pitch;
-    float* red = reinterpret_cast<float*>(tw + w);
+    float2* twn = tw + w;                                                 // e^{+2 pi i j / nx}, odd windows only
+    float* red = reinterpret_cast<float*>(twn + (odd ? w : 0));
     unsigned short* pos_of = reinterpret_cast<unsigned short*>(red + 64);     // bin k -> position (digit reversal)
     unsigned short* bin_at = pos_of + w;                                      // position -> bin
     const bool fft = p.n_stages > 0;
@@ -394,6 +399,10 @@ __global__ void __launch_bounds__(BIG ? kGenericThreads : 256, BIG ? 1 : 4) gene
         const int q = fft ? generic_pos(p, k, w) : k;
         pos_of[k] = static_cast<unsigned short>(q);
         bin_at[q] = static_cast<unsigned short>(k);
+        if (odd && k < nx) {
+            sincospi(2.0 * k / nx, &s, &c);
+            twn[k] = make_float2(static_cast<float>(c), static_cast<float>(s));
+        }
     }
     __syncthreads();
     const int per_pair = p.n_rows * p.n_cols;
@@ -532,29 +541,67 @@ __global__ void __launch_bounds__(BIG ? kGenericThreads : 256, BIG ? 1 : 4) gene
         }
         __syncthreads();
         // ---- inverse transform (real result) ---------------------------------------------------
-        if (fft) {
-            generic_fft_dit<BIG>(p, Z, tw, w, pitch, true);
-            generic_fft_dit<BIG>(p, Z, tw, w, pitch, false);
+        if (fft) generic_fft_dit<BIG>(p, Z, tw, w, pitch, true);
+        else generic_lines(Z, tw, w, pitch, true, true);
+        if (!odd) {
+            if (fft) generic_fft_dit<BIG>(p, Z, tw, w, pitch, false);
+            else generic_lines(Z, tw, w, pitch, false, true);
         } else {
-            generic_lines(Z, tw, w, pitch, true, true);
-            generic_lines(Z, tw, w, pitch, false, true);
+            // Column y now holds w Q[y][kx] (direct sums) or its conjugate (FFT path), kx at position pos_of[kx].  Row y of
+            // the map: out[s] = Re Q0 + (-1)^s Re Q_{n/2} + 2 sum_{0 < k < n/2} Re(Q_k e^{2 pi i k s / n}), n = w - 1 (what a
+            // c2r transform computes: the imaginary parts of bins 0 and n/2 do not enter).  A warp takes a row, its lanes
+            // the samples s, s + 32, ...; the results replace the row.
+            const float sgn = fft ? -1.f : 1.f;
+            const int hn = nx / 2;
+            for (int y = ty; y < w; y += nwy) {
+                float2* row = Z + y * pitch;
+                float acc[8];
+                int idx[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const int sidx = tx + 32 * t;
+                    acc[t] = row[pos_of[0]].x + ((sidx & 1) ? -1.f : 1.f) * row[pos_of[hn]].x;
+                    idx[t] = sidx % nx;                       // (k s) mod n for k = 1
+                }
+                for (int k = 1; k < hn; ++k) {
+                    const float2 q = row[pos_of[k]];
+                    const float qr = 2.f * q.x, qi = 2.f * sgn * q.y;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const int sidx = tx + 32 * t;
+                        if (sidx < nx) {
+                            const float2 e = twn[idx[t]];
+                            acc[t] = fmaf(qr, e.x, fmaf(-qi, e.y, acc[t]));
+                            idx[t] += sidx;
+                            if (idx[t] >= nx) idx[t] -= nx;
+                        }
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    if (tx + 32 * t < nx) row[tx + 32 * t] = make_float2(acc[t], 0.f);
+            }
+            __syncthreads();
         }
-        const float scale = norm / (static_cast<float>(w) * static_cast<float>(w));
+        const float scale = norm / (static_cast<float>(w) * static_cast<float>(nx));
         float mn = 0.f;
         if (p.subtract_min) {
             float m = FLT_MAX;
             for (int i = ty; i < w; i += nwy)
-                for (int j = tx; j < w; j += 32) m = fminf(m, Z[i * pitch + j].x * scale);
+                for (int j = tx; j < nx; j += 32) m = fminf(m, Z[i * pitch + j].x * scale);
             mn = block_reduce(m, red, 1);
         }
-        float* out = p.corr_out + wq * w * w;
+        // fft-shifted map [w][nx] (torch.fft.fftshift: element i comes from (i - N / 2) mod N on either axis)
+        float* out = p.corr_out + wq * w * nx;
+        const int hx = nx / 2, hy = w - half;
         for (int i = ty; i < w; i += nwy) {
-            const int si = i >= half ? i - half : i + half;              // (i, j) = position in the fft-shifted map
-            for (int j = tx; j < w; j += 32) {
-                const int sj = j >= half ? j - half : j + half;
+            const int si = i + hy >= w ? i + hy - w : i + hy;
+            for (int j = tx; j < nx; j += 32) {
+                const int sj = j >= hx ? j - hx : j + hx;
                 const float val = Z[si * pitch + sj].x * scale;
                 // NaN maps (black window divided by its zero mean) stay NaN: fminf drops NaNs, the subtraction keeps them
-                out[i * w + j] = p.subtract_min ? val - mn : val;
+                out[i * nx + j] = p.subtract_min ? val - mn : val;
             }
         }
         __syncthreads();
@@ -582,11 +629,14 @@ __global__ void generic_glue_kernel(const double* __restrict__ du, const double*
     }
 }
 
-inline bool generic_window_ok(int wind) { return wind >= 4 && wind <= kGenericMaxWindow && wind % 2 == 0; }
+// any size 4..256: odd windows give the reference's [w, w - 1] maps
+inline bool generic_window_ok(int wind) { return wind >= 4 && wind <= kGenericMaxWindow; }
+inline int generic_map_cols(int wind) { return (wind & 1) ? wind - 1 : wind; }
 
 inline size_t generic_smem_bytes(int w) {
-    const size_t z = (w <= kGenericMaxSharedWindow) ? static_cast<size_t>(w) * (w + 1) * sizeof(float2) : 0;
-    return z + static_cast<size_t>(w) * sizeof(float2) + 64 * sizeof(float) + 2 * static_cast<size_t>(w) * sizeof(unsigned short);
+    const size_t z = (w <= kGenericMaxSharedWindow) ? static_cast<size_t>(w) * (w | 1) * sizeof(float2) : 0;
+    return z + static_cast<size_t>(w) * sizeof(float2) * ((w & 1) ? 2 : 1) + 64 * sizeof(float) +
+           2 * static_cast<size_t>(w) * sizeof(unsigned short);
 }
 
 // threads per window: small windows are latency-bound by their ~25 block-wide phases, so they get small blocks
@@ -634,7 +684,7 @@ inline int generic_launch(const GenericParams& gp_in, cudaStream_t s) {
     gp.zglobal = nullptr;
     if (gz) {           // stream-ordered scratch: grid slabs of w (w + 1) complex values (78 MB for 256 px on 148 SMs)
         err = cudaMallocAsync(reinterpret_cast<void**>(&gp.zglobal),
-                              static_cast<size_t>(grid) * gp.wind * (gp.wind + 1) * sizeof(float2), s);
+                              static_cast<size_t>(grid) * gp.wind * (gp.wind | 1) * sizeof(float2), s);
         if (err != cudaSuccess) return static_cast<int>(err);
     }
     kern<<<static_cast<unsigned>(grid), threads, smem, s>>>(gp);
@@ -667,7 +717,8 @@ inline int run_generic_pass(const unsigned char* fa, const unsigned char* fb, in
     gp.normalize = p.first_pass;
     gp.subtract_min = 1;
     // scratch: maps of one chunk + du, dv of the whole pass
-    const long long map_elems = static_cast<long long>(wind) * wind;
+    const int map_cols = generic_map_cols(wind);
+    const long long map_elems = static_cast<long long>(wind) * map_cols;
     long long chunk = (256ll << 20) / (map_elems * 4);                    // <= 256 MB of maps at a time
     if (chunk < 1) chunk = 1;
     if (chunk > n_total) chunk = n_total;
@@ -700,7 +751,7 @@ inline int run_generic_pass(const unsigned char* fa, const unsigned char* fb, in
         rc = generic_launch(gp, s);
         if (rc) break;
         corr_to_disp_kernel<float><<<grid_for(n * 32, 128), 128, 0, s>>>(
-            maps, n, wind, wind, p.validate, p.val_ratio, 3, du + first, dv + first, p.mask ? p.mask + first : nullptr);
+            maps, n, wind, map_cols, p.validate, p.val_ratio, 3, du + first, dv + first, p.mask ? p.mask + first : nullptr);
         count_launch();
         rc = static_cast<int>(cudaGetLastError());
     }

@@ -53,10 +53,9 @@ def _geometry(frame_shape, wind, overlap) -> PassGeometry:
     if wind > frame_shape[-2] or wind > frame_shape[-1]:
         raise ValueError("window size cannot be larger than the image")
     if not window_supported(wind):
-        raise ValueError(f"interrogation window must be an even size of 4..{MAX_WINDOW} px (got {wind}): "
-                         "16/32/64 px run the fused in-register FFT kernels, other even sizes the "
-                         "general direct-DFT kernel; odd sizes are not supported (the reference's "
-                         "irfft2 returns a [w, w-1] map for them) and there is no CPU fallback")
+        raise ValueError(f"interrogation window must be 4..{MAX_WINDOW} px (got {wind}): 16/32/64 px run the fused "
+                         "in-register FFT kernels, other sizes the general mixed-radix kernel; there is no "
+                         "CPU fallback")
     n_rows, n_cols = (int(v) for v in get_field_shape(frame_shape, wind, overlap)[-2:])
     x, y = get_coordinates(frame_shape, wind, overlap)
     return PassGeometry(wind, overlap, n_rows, n_cols, x, y)

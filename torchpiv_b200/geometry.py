@@ -16,13 +16,14 @@ import numpy as np
 __all__ = ["get_field_shape", "get_coordinates", "spline_operator"]
 
 FUSED_WINDOWS = (16, 32, 64)          # fused in-register FFT kernels
-MAX_WINDOW = 256                      # general-size path (mixed-radix FFT in shared memory): any even size up to this
+MAX_WINDOW = 256                      # general-size path (mixed-radix FFT in shared memory): any size up to this
 SUPPORTED_WINDOWS = FUSED_WINDOWS     # kept for callers that ask which sizes take the fast path
 
 
 def window_supported(wind: int) -> bool:
-    """Sizes the library can process: even, 4..256 px (16/32/64 px take the fused kernels)."""
-    return int(wind) == wind and 4 <= wind <= MAX_WINDOW and wind % 2 == 0
+    """Sizes the library can process: 4..256 px (16/32/64 px take the fused kernels; odd sizes give the
+    reference's [w, w-1] correlation maps)."""
+    return int(wind) == wind and 4 <= wind <= MAX_WINDOW
 
 
 def get_field_shape(image_size, search_area_size, overlap):
