@@ -124,6 +124,22 @@ def test_halving_into_an_odd_window(T, golden, mode):
                 max_ill_valid=0.05)
 
 
+@pytest.mark.parametrize("mode", ["CWS", "DWS"])
+def test_plan_with_an_odd_pass_vs_oracle(T, mode):
+    """Device-resident 100 -> 50 -> 25 px plan (general kernel on every pass, the last one on odd windows) vs the
+    oracle's chained passes."""
+    a, b = cases.small_pair(seed=7, kind="vortex")
+    plan = T.PIVPlan(a.shape, 100, 50, 3, mode, 2.0, device="cuda:0")
+    assert [g.wind for g in plan.passes] == [100, 50, 25]
+    plan.run(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
+    ou, ov, _, _, om, hist = O.piv_passes(a, b, 100, 50, 3, mode)
+    for k, (hu, hv, hm) in enumerate(hist):
+        du, dv, dm = (t[0].cpu().numpy() for t in plan.pass_results(k, 1))
+        assert du.shape == hu.shape
+        assert (dm.astype(bool) == hm).mean() > 0.95
+        assert np.quantile(np.abs(du - hu), 0.9) < 1e-4 and np.quantile(np.abs(dv - hv), 0.9) < 1e-4, (mode, k)
+
+
 def test_offline_piv_with_scale_1p5(T, golden, tmp_path):
     from torchpiv_b200 import synth
     g = golden("general_sizes.npz")
