@@ -188,6 +188,24 @@ def test_multipass_scale_1p5_function_boundary(golden, mode):
         x, y = x1, y1
 
 
+@pytest.mark.parametrize("mode", ["CWS", "DWS"])
+def test_halving_into_an_odd_window_function_boundary(golden, mode):
+    """50 -> 25 px: the second pass runs on odd windows, whose maps are [25, 24] in the reference (irfft2 without a
+    size, PB:255); fed with the reference's first-pass output."""
+    g = golden("general_sizes.npz")
+    a, b = cases.small_pair(seed=3, kind="vortex", zero_patch=True)
+    x, y = O.get_coordinates(a.shape, 50, 25)
+    u0, v0, m0 = (g[f"odd{mode}_p0_{k}"].copy() for k in ("u", "v", "mask"))
+    fn = O.ITER_MODES[mode](a.shape, 25, 12)
+    u, v, x1, y1, m = fn(a, b, x, y, u0, v0, m0)
+    assert fn.last_corr.shape[1:] == (25, 24)
+    assert np.array_equal(x1, g[f"odd{mode}_p1_x"]) and np.array_equal(y1, g[f"odd{mode}_p1_y"])
+    assert (m != g[f"odd{mode}_p1_mask"]).mean() <= 0.01
+    for got, key in ((u, "u"), (v, "v")):
+        err = np.abs(got - g[f"odd{mode}_p1_{key}"])
+        assert np.quantile(err, 0.98) < TOL32 and np.quantile(err, 0.995) < 1e-3
+
+
 # ------------------------------------------------------------------------------------------
 # oracle/torch_eager.py: the eager-PyTorch restatement that bench.py times on the GPU as the
 # "stock torch-CUDA path" comparator.  Pinned here with device="cpu".
